@@ -1,0 +1,630 @@
+// api.cu — the C-ABI of include/flatdd_b200.h on top of the sm_100a kernels in kernels.cuh.
+// No CPU fallback: every compute entry point needs a CUDA device and fails loudly without one.
+#include "flatdd_b200.h"
+#include "gate_compile.hpp"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace fddb200;
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int fail(int code, const std::string& msg) {
+    g_lastError = msg;
+    return code;
+}
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define CUDA_TRY(expr)                                                                                       \
+    do {                                                                                                     \
+        const cudaError_t err__ = (expr);                                                                    \
+        if (err__ != cudaSuccess) {                                                                          \
+            throw CudaError(std::string(#expr) + ": " + cudaGetErrorName(err__) + " (" + cudaGetErrorString(err__) + ")"); \
+        }                                                                                                    \
+    } while (0)
+
+// Runs `body`, mapping exceptions to error codes.
+template <class F> int guarded(F&& body) {
+    try {
+        body();
+        return FDD_OK;
+    } catch (const CudaError& e) {
+        return fail(FDD_ERR_CUDA, e.what());
+    } catch (const std::invalid_argument& e) {
+        return fail(FDD_ERR_INVALID, e.what());
+    } catch (const std::length_error& e) {
+        return fail(FDD_ERR_TOO_DENSE, e.what());
+    } catch (const std::logic_error& e) {
+        return fail(FDD_ERR_STATE, e.what());
+    } catch (const std::runtime_error& e) {
+        return fail(FDD_ERR_INVALID, e.what());
+    } catch (const std::exception& e) {
+        return fail(FDD_ERR_INVALID, e.what());
+    }
+}
+
+constexpr size_t kSmemBudget = 227 * 1024;
+constexpr size_t kTableSmemLimit = 96 * 1024;
+
+} // namespace
+
+struct fdd_gate {
+    CompiledGate host;
+    int device = 0;
+    // device copies
+    UpperNode* dUpper = nullptr;
+    double2* dSubW = nullptr;
+    uint8_t* dSubCol = nullptr;
+    int32_t* dSubK = nullptr;
+    uint8_t* dSubFlags = nullptr;
+    void* dBlob = nullptr; // one allocation holding all of the above
+};
+
+struct fdd_ctx {
+    int n = 0;
+    int nLocal = 0;
+    int device = 0;
+    int rank = 0;
+    int world = 1;
+    int worldBits = 0;
+    double2* buf[2] = {nullptr, nullptr};
+    int cur = 0;
+    bool hasState = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timing = false;
+    float lastMs = 0.0f;
+    uint64_t launches = 0;
+    int smCount = 148;
+    // tunables
+    int variant = 1;
+    int warpsPerCta = 8;
+    int ctasPerSm = 0; // 0 = as many as shared memory allows (capped)
+    int prefetch = 8;
+    // scratch
+    double* dPartial = nullptr;
+    double* dNorm = nullptr;
+    std::vector<int32_t> logicalToPhysical;
+    // multi-GPU
+    const double2* peerBuf[2][kMaxPeers] = {};
+    void* comm = nullptr;
+
+    [[nodiscard]] uint64_t localDim() const { return uint64_t{1} << nLocal; }
+};
+
+namespace {
+
+void useDevice(const fdd_ctx* c) { CUDA_TRY(cudaSetDevice(c->device)); }
+
+struct Timed {
+    fdd_ctx* c;
+    explicit Timed(fdd_ctx* ctx) : c(ctx) {
+        if (c->timing) cudaEventRecord(c->ev0, c->stream);
+    }
+    ~Timed() {
+        if (c->timing) {
+            cudaEventRecord(c->ev1, c->stream);
+            cudaEventSynchronize(c->ev1);
+            cudaEventElapsedTime(&c->lastMs, c->ev0, c->ev1);
+        }
+    }
+};
+
+int gridFor(const fdd_ctx* c, uint64_t items, int block) {
+    const uint64_t want = (items + block - 1) / block;
+    return static_cast<int>(std::max<uint64_t>(1, std::min<uint64_t>(want, static_cast<uint64_t>(c->smCount) * 8)));
+}
+
+void uploadGate(fdd_gate* g, cudaStream_t stream) {
+    const CompiledGate& h = g->host;
+    const size_t bUpper = h.upper.size() * sizeof(UpperNode);
+    const size_t nEnt = static_cast<size_t>(h.nSub) * h.kMax * 32;
+    const size_t bW = nEnt * 16, bK = static_cast<size_t>(h.nSub) * 4, bCol = nEnt, bF = static_cast<size_t>(h.nSub);
+    const size_t total = bUpper + bW + bK + bCol + bF + 64;
+    std::vector<unsigned char> blob(total, 0);
+    size_t off = 0;
+    auto put = [&](const void* src, size_t bytes) {
+        const size_t at = off;
+        if (bytes != 0) std::memcpy(blob.data() + at, src, bytes);
+        off += bytes;
+        return at;
+    };
+    const size_t oUpper = put(h.upper.data(), bUpper);
+    const size_t oW = put(h.subW.data(), bW);
+    const size_t oK = put(h.subK.data(), bK);
+    const size_t oCol = put(h.subCol.data(), bCol);
+    const size_t oF = put(h.subFlags.data(), bF);
+    CUDA_TRY(cudaMallocAsync(&g->dBlob, total, stream));
+    // pageable source: the copy is staged by the runtime before the call returns
+    CUDA_TRY(cudaMemcpyAsync(g->dBlob, blob.data(), total, cudaMemcpyHostToDevice, stream));
+    auto* base = static_cast<unsigned char*>(g->dBlob);
+    g->dUpper = reinterpret_cast<UpperNode*>(base + oUpper);
+    g->dSubW = reinterpret_cast<double2*>(base + oW);
+    g->dSubK = reinterpret_cast<int32_t*>(base + oK);
+    g->dSubCol = base + oCol;
+    g->dSubFlags = base + oF;
+}
+
+void launchWalk(fdd_ctx* c, const fdd_gate* g) {
+    const CompiledGate& h = g->host;
+    if (h.n != c->n) throw std::invalid_argument("gate has " + std::to_string(h.n) + " qubits, context has " + std::to_string(c->n));
+    if (!c->hasState) throw std::logic_error("no state: call fdd_convert / fdd_set_state / fdd_set_zero_state first");
+    if (c->world > 1 && h.topLevel >= c->nLocal && c->peerBuf[0][0] == nullptr) {
+        throw std::logic_error("gate acts on a global qubit but the shards are not connected (fdd_comm_init)");
+    }
+    WalkParams p{};
+    p.y = c->buf[c->cur];
+    p.z = c->buf[c->cur ^ 1];
+    for (int r = 0; r < kMaxPeers; ++r) p.peerY[r] = c->peerBuf[c->cur][r];
+    if (c->world == 1) p.peerY[0] = p.y;
+    p.upper = g->dUpper;
+    p.nUpper = static_cast<int>(h.upper.size());
+    p.subW = g->dSubW;
+    p.subCol = g->dSubCol;
+    p.subK = g->dSubK;
+    p.subFlags = g->dSubFlags;
+    p.nSub = h.nSub;
+    p.kMax = h.kMax;
+    p.root = h.root;
+    p.rootW = make_double2(h.rootW[0], h.rootW[1]);
+    p.nLocal = c->nLocal;
+    p.segBits = std::min(h.segBits, c->nLocal);
+    if (p.segBits != h.segBits) throw std::invalid_argument("shard too small for this gate (fewer than 5 local qubits)");
+    p.maxPaths = h.maxPaths;
+    p.stackCap = h.stackCap;
+    p.rank = static_cast<uint32_t>(c->rank);
+    p.worldBits = c->worldBits;
+    p.nSeg = static_cast<uint32_t>(c->localDim() >> p.segBits);
+    p.nTiles = (p.nSeg + 31) / 32;
+    int D = c->prefetch;
+    if (D != 1 && D != 2 && D != 4 && D != 8 && D != 16) D = 8;
+    p.prefetch = D;
+    const int variant = c->variant == 0 ? 0 : 1;
+
+    const size_t tableBytes = walkTableSmem(p.nUpper, p.nSub, p.kMax);
+    p.tablesInSmem = tableBytes <= kTableSmemLimit ? 1 : 0;
+    const size_t fixed = p.tablesInSmem ? tableBytes : 0;
+    const size_t perWarp = walkWarpSmem(p.maxPaths, p.stackCap, variant == 1 ? D : 0);
+    int warps = std::max(1, std::min(c->warpsPerCta, 16));
+    while (warps > 1 && fixed + warps * perWarp > kSmemBudget) warps >>= 1;
+    if (fixed + warps * perWarp > kSmemBudget) {
+        throw std::length_error("gate too dense for one launch: " + std::to_string(h.maxPaths) +
+                                " source segments per output segment; split the fused gate");
+    }
+    const size_t smem = fixed + warps * perWarp;
+    int perSm = static_cast<int>(kSmemBudget / std::max<size_t>(smem, 1));
+    perSm = std::max(1, std::min(perSm, std::max(1, 48 / warps))); // at most 48 resident warps per SM
+    if (c->ctasPerSm > 0) perSm = std::min(perSm, c->ctasPerSm);
+    const uint32_t ctasWanted = (p.nTiles + warps - 1) / warps;
+    const int grid = static_cast<int>(std::max<uint32_t>(1, std::min<uint32_t>(ctasWanted, static_cast<uint32_t>(c->smCount * perSm))));
+
+    Timed t(c);
+    if (variant == 0) {
+        CUDA_TRY(cudaFuncSetAttribute(dmavm_walk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
+        dmavm_walk_kernel<0><<<grid, warps * 32, smem, c->stream>>>(p);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(dmavm_walk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
+        dmavm_walk_kernel<1><<<grid, warps * 32, smem, c->stream>>>(p);
+    }
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    c->cur ^= 1;
+}
+
+void freeGate(fdd_gate* g, cudaStream_t stream) {
+    if (g == nullptr) return;
+    if (g->dBlob != nullptr) {
+        cudaSetDevice(g->device);
+        if (stream != nullptr) {
+            cudaFreeAsync(g->dBlob, stream);
+        } else {
+            cudaFree(g->dBlob);
+        }
+    }
+    delete g;
+}
+
+fdd_ctx* createCtx(int nQubits, int device, int rank, int world) {
+    if (nQubits < 1 || nQubits > 40) throw std::invalid_argument("n_qubits must be in [1, 40]");
+    if (world < 1 || world > kMaxPeers || (world & (world - 1)) != 0) throw std::invalid_argument("world_size must be 1, 2, 4 or 8");
+    if (rank < 0 || rank >= world) throw std::invalid_argument("rank out of range");
+    int worldBits = 0;
+    while ((1 << worldBits) < world) ++worldBits;
+    if (nQubits - worldBits < 5 && world > 1) throw std::invalid_argument("a shard must hold at least 5 qubits");
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    if (count == 0) throw CudaError("no CUDA device: flatdd_b200 has no CPU fallback");
+    if (device < 0 || device >= count) throw std::invalid_argument("device index out of range");
+    auto ctx = new fdd_ctx();
+    try {
+        ctx->n = nQubits;
+        ctx->rank = rank;
+        ctx->world = world;
+        ctx->worldBits = worldBits;
+        ctx->nLocal = nQubits - worldBits;
+        ctx->device = device;
+        CUDA_TRY(cudaSetDevice(device));
+        cudaDeviceProp prop{};
+        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        ctx->smCount = prop.multiProcessorCount;
+        if (prop.major < 10) {
+            throw CudaError(std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                            "; this library is built for sm_100a only");
+        }
+        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&ctx->ev0));
+        CUDA_TRY(cudaEventCreate(&ctx->ev1));
+        const size_t bytes = sizeof(double2) << ctx->nLocal;
+        CUDA_TRY(cudaMalloc(&ctx->buf[0], bytes));
+        CUDA_TRY(cudaMalloc(&ctx->buf[1], bytes));
+        CUDA_TRY(cudaMalloc(&ctx->dPartial, sizeof(double) * 4096));
+        CUDA_TRY(cudaMalloc(&ctx->dNorm, sizeof(double)));
+        ctx->logicalToPhysical.resize(static_cast<size_t>(nQubits));
+        for (int q = 0; q < nQubits; ++q) ctx->logicalToPhysical[static_cast<size_t>(q)] = q;
+    } catch (...) {
+        fdd_destroy(ctx);
+        throw;
+    }
+    return ctx;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* fdd_version(void) { return "flatdd_b200 0.1 (sm_100a)"; }
+const char* fdd_last_error(void) { return g_lastError.c_str(); }
+
+int fdd_device_count(int* count) {
+    return guarded([&] {
+        if (count == nullptr) throw std::invalid_argument("count is null");
+        CUDA_TRY(cudaGetDeviceCount(count));
+        if (*count == 0) throw CudaError("no CUDA device: flatdd_b200 has no CPU fallback");
+    });
+}
+
+int fdd_create(int n_qubits, int device, fdd_ctx** out) { return fdd_create_sharded(n_qubits, device, 0, 1, out); }
+
+int fdd_create_sharded(int n_qubits, int device, int rank, int world_size, fdd_ctx** out) {
+    return guarded([&] {
+        if (out == nullptr) throw std::invalid_argument("out is null");
+        *out = nullptr;
+        *out = createCtx(n_qubits, device, rank, world_size);
+    });
+}
+
+int fdd_destroy(fdd_ctx* ctx) {
+    if (ctx == nullptr) return FDD_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream != nullptr) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->buf[0]);
+    cudaFree(ctx->buf[1]);
+    cudaFree(ctx->dPartial);
+    cudaFree(ctx->dNorm);
+    if (ctx->ev0 != nullptr) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1 != nullptr) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream != nullptr) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return FDD_OK;
+}
+
+int fdd_n_qubits(const fdd_ctx* ctx) { return ctx != nullptr ? ctx->n : 0; }
+int fdd_n_local_qubits(const fdd_ctx* ctx) { return ctx != nullptr ? ctx->nLocal : 0; }
+
+int fdd_synchronize(fdd_ctx* ctx) {
+    return guarded([&] {
+        if (ctx == nullptr) throw std::invalid_argument("ctx is null");
+        useDevice(ctx);
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int fdd_set_option(fdd_ctx* ctx, const char* key, long value) {
+    return guarded([&] {
+        if (ctx == nullptr || key == nullptr) throw std::invalid_argument("null argument");
+        const std::string k = key;
+        if (k == "dmavm_variant") ctx->variant = static_cast<int>(value);
+        else if (k == "warps_per_cta") ctx->warpsPerCta = static_cast<int>(value);
+        else if (k == "ctas_per_sm") ctx->ctasPerSm = static_cast<int>(value);
+        else if (k == "prefetch") ctx->prefetch = static_cast<int>(value);
+        else throw std::invalid_argument("unknown option " + k);
+    });
+}
+
+int fdd_comm_unique_id(void* /*id128*/) { return fail(FDD_ERR_COMM, "multi-GPU exchange is not built in this revision"); }
+int fdd_comm_init(fdd_ctx* /*ctx*/, const void* /*id128*/) { return fail(FDD_ERR_COMM, "multi-GPU exchange is not built in this revision"); }
+
+int fdd_convert(fdd_ctx* ctx, const fdd_vecdd* dd) {
+    return guarded([&] {
+        if (ctx == nullptr || dd == nullptr) throw std::invalid_argument("null argument");
+        validate(*dd);
+        if (dd->n_qubits != ctx->n) throw std::invalid_argument("vector DD has " + std::to_string(dd->n_qubits) + " qubits, context has " + std::to_string(ctx->n));
+        useDevice(ctx);
+        std::vector<VecNode> table(static_cast<size_t>(dd->n_nodes));
+        for (int32_t u = 0; u < dd->n_nodes; ++u) {
+            VecNode& nd = table[static_cast<size_t>(u)];
+            nd.level = dd->level[u];
+            nd.pad = 0;
+            for (int b = 0; b < 2; ++b) {
+                const size_t e = 2 * static_cast<size_t>(u) + static_cast<size_t>(b);
+                const bool zero = dd->weight[2 * e] == 0.0 && dd->weight[2 * e + 1] == 0.0;
+                nd.child[b] = zero ? FDD_TERMINAL : dd->child[e];
+                nd.w[b] = zero ? make_double2(0.0, 0.0) : make_double2(dd->weight[2 * e], dd->weight[2 * e + 1]);
+            }
+        }
+        VecNode* dTable = nullptr;
+        const size_t tableBytes = table.size() * sizeof(VecNode);
+        CUDA_TRY(cudaMallocAsync(&dTable, tableBytes, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(dTable, table.data(), tableBytes, cudaMemcpyHostToDevice, ctx->stream));
+        ConvertParams p{};
+        p.nodes = dTable;
+        p.nNodes = dd->n_nodes;
+        p.root = dd->root;
+        p.rootW = make_double2(dd->root_weight[0], dd->root_weight[1]);
+        p.nQubits = ctx->n;
+        p.nLocal = ctx->nLocal;
+        p.segBits = std::min(5, ctx->nLocal);
+        p.rank = static_cast<uint32_t>(ctx->rank);
+        p.nSeg = static_cast<uint32_t>(ctx->localDim() >> p.segBits);
+        p.nTiles = (p.nSeg + 31) / 32;
+        p.tableInSmem = tableBytes <= 160 * 1024 ? 1 : 0;
+        p.out = ctx->buf[ctx->cur ^ 1];
+        const size_t smem = p.tableInSmem ? tableBytes : 0;
+        const int warps = 8;
+        int perSm = smem == 0 ? 4 : static_cast<int>(std::max<size_t>(1, std::min<size_t>(4, kSmemBudget / smem)));
+        const uint32_t ctasWanted = (p.nTiles + warps - 1) / warps;
+        const int grid = static_cast<int>(std::max<uint32_t>(1, std::min<uint32_t>(ctasWanted, static_cast<uint32_t>(ctx->smCount * perSm))));
+        {
+            Timed t(ctx);
+            CUDA_TRY(cudaFuncSetAttribute(convert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
+            convert_kernel<<<grid, warps * 32, smem, ctx->stream>>>(p);
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaFreeAsync(dTable, ctx->stream));
+        ctx->launches++;
+        ctx->cur ^= 1;
+        ctx->hasState = true;
+        for (int q = 0; q < ctx->n; ++q) ctx->logicalToPhysical[static_cast<size_t>(q)] = q;
+    });
+}
+
+int fdd_gate_compile(fdd_ctx* ctx, const fdd_matdd* gate, fdd_gate** out) {
+    return guarded([&] {
+        if (ctx == nullptr || gate == nullptr || out == nullptr) throw std::invalid_argument("null argument");
+        *out = nullptr;
+        useDevice(ctx);
+        auto g = new fdd_gate();
+        try {
+            g->host = compileGate(*gate);
+            g->device = ctx->device;
+            uploadGate(g, ctx->stream);
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        } catch (...) {
+            freeGate(g, nullptr);
+            throw;
+        }
+        *out = g;
+    });
+}
+
+int fdd_gate_apply(fdd_ctx* ctx, const fdd_gate* gate) {
+    return guarded([&] {
+        if (ctx == nullptr || gate == nullptr) throw std::invalid_argument("null argument");
+        useDevice(ctx);
+        launchWalk(ctx, gate);
+    });
+}
+
+int fdd_gate_free(fdd_gate* gate) {
+    freeGate(gate, nullptr);
+    return FDD_OK;
+}
+
+long fdd_gate_info(const fdd_gate* gate, const char* key) {
+    if (gate == nullptr || key == nullptr) return -1;
+    const std::string k = key;
+    const CompiledGate& h = gate->host;
+    if (k == "kind") return h.diagonal ? 1 : 0;
+    if (k == "max_paths") return h.maxPaths;
+    if (k == "max_sub_k") return h.kMax;
+    if (k == "upper_nodes") return static_cast<long>(h.upper.size());
+    if (k == "sub_tables") return h.nSub;
+    if (k == "nnz_per_row_max") return h.nnzRowMax;
+    if (k == "top_level") return h.topLevel;
+    if (k == "upper_depth") return h.upperDepth;
+    if (k == "stack_cap") return h.stackCap;
+    return -1;
+}
+
+int fdd_apply(fdd_ctx* ctx, const fdd_matdd* gate) {
+    return guarded([&] {
+        if (ctx == nullptr || gate == nullptr) throw std::invalid_argument("null argument");
+        useDevice(ctx);
+        auto g = new fdd_gate();
+        try {
+            g->host = compileGate(*gate);
+            g->device = ctx->device;
+            uploadGate(g, ctx->stream);
+            launchWalk(ctx, g);
+        } catch (...) {
+            freeGate(g, ctx->stream);
+            throw;
+        }
+        freeGate(g, ctx->stream); // stream ordered: released after the kernel has run
+    });
+}
+
+int fdd_ddarr_multiply(const fdd_matdd* gate, const double* y_real, const double* y_imag, double* z_real, double* z_imag,
+                       size_t n_dim, int device) {
+    if (gate == nullptr) return fail(FDD_ERR_INVALID, "gate is null");
+    if (n_dim != (size_t{1} << gate->n_qubits)) return fail(FDD_ERR_INVALID, "n_dim != 2^n_qubits");
+    fdd_ctx* ctx = nullptr;
+    int rc = fdd_create(gate->n_qubits, device, &ctx);
+    if (rc != FDD_OK) return rc;
+    rc = fdd_set_state(ctx, y_real, y_imag);
+    if (rc == FDD_OK) rc = fdd_apply(ctx, gate);
+    if (rc == FDD_OK) rc = fdd_get_state(ctx, z_real, z_imag);
+    fdd_destroy(ctx);
+    return rc;
+}
+
+int fdd_mac_count(const fdd_matdd* gate, uint64_t* nnz) {
+    return guarded([&] {
+        if (gate == nullptr || nnz == nullptr) throw std::invalid_argument("null argument");
+        validate(*gate);
+        *nnz = macCount(*gate);
+    });
+}
+int fdd_cost_ip(const fdd_matdd* gate, unsigned n_thread_exp, uint64_t* cost) {
+    return guarded([&] {
+        if (gate == nullptr || cost == nullptr) throw std::invalid_argument("null argument");
+        validate(*gate);
+        *cost = costIP(*gate, n_thread_exp);
+    });
+}
+int fdd_cost_op1(const fdd_matdd* gate, unsigned n_thread_exp, uint64_t* cost) {
+    return guarded([&] {
+        if (gate == nullptr || cost == nullptr) throw std::invalid_argument("null argument");
+        validate(*gate);
+        if (static_cast<int>(n_thread_exp) >= gate->n_qubits) throw std::invalid_argument("n_thread_exp must be below n_qubits");
+        *cost = costOP1(*gate, n_thread_exp);
+    });
+}
+int fdd_cost_gpu(const fdd_matdd* gate, double hbm_gbs, double fp64_gflops, double* nanoseconds) {
+    return guarded([&] {
+        if (gate == nullptr || nanoseconds == nullptr) throw std::invalid_argument("null argument");
+        const CompiledGate c = compileGate(*gate);
+        const size_t perWarp = walkWarpSmem(c.maxPaths, c.stackCap, 8);
+        const size_t tables = walkTableSmem(static_cast<int>(c.upper.size()), c.nSub, c.kMax);
+        if ((tables <= kTableSmemLimit ? tables : 0) + perWarp > kSmemBudget) throw std::length_error("gate too dense for one launch");
+        *nanoseconds = costGpuNs(c, hbm_gbs, fp64_gflops);
+    });
+}
+
+int fdd_get_state(fdd_ctx* ctx, double* real, double* imag) {
+    return guarded([&] {
+        if (ctx == nullptr || real == nullptr || imag == nullptr) throw std::invalid_argument("null argument");
+        if (!ctx->hasState) throw std::logic_error("no state");
+        useDevice(ctx);
+        const uint64_t dim = ctx->localDim();
+        // de-interleave into the idle ping-pong buffer, then two planar copies
+        auto* planar = reinterpret_cast<double*>(ctx->buf[ctx->cur ^ 1]);
+        deinterleave_kernel<<<gridFor(ctx, dim, 256), 256, 0, ctx->stream>>>(ctx->buf[ctx->cur], planar, planar + dim, dim);
+        CUDA_TRY(cudaGetLastError());
+        ctx->launches++;
+        CUDA_TRY(cudaMemcpyAsync(real, planar, dim * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(imag, planar + dim, dim * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int fdd_set_state(fdd_ctx* ctx, const double* real, const double* imag) {
+    return guarded([&] {
+        if (ctx == nullptr || real == nullptr || imag == nullptr) throw std::invalid_argument("null argument");
+        useDevice(ctx);
+        const uint64_t dim = ctx->localDim();
+        auto* planar = reinterpret_cast<double*>(ctx->buf[ctx->cur]);
+        CUDA_TRY(cudaMemcpyAsync(planar, real, dim * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(planar + dim, imag, dim * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        interleave_kernel<<<gridFor(ctx, dim, 256), 256, 0, ctx->stream>>>(planar, planar + dim, ctx->buf[ctx->cur ^ 1], dim);
+        CUDA_TRY(cudaGetLastError());
+        ctx->launches++;
+        ctx->cur ^= 1;
+        ctx->hasState = true;
+        for (int q = 0; q < ctx->n; ++q) ctx->logicalToPhysical[static_cast<size_t>(q)] = q;
+    });
+}
+
+int fdd_set_zero_state(fdd_ctx* ctx) {
+    return guarded([&] {
+        if (ctx == nullptr) throw std::invalid_argument("ctx is null");
+        useDevice(ctx);
+        const uint64_t dim = ctx->localDim();
+        zero_state_kernel<<<gridFor(ctx, dim, 256), 256, 0, ctx->stream>>>(ctx->buf[ctx->cur], dim, ctx->rank == 0 ? 1 : 0);
+        CUDA_TRY(cudaGetLastError());
+        ctx->launches++;
+        ctx->hasState = true;
+        for (int q = 0; q < ctx->n; ++q) ctx->logicalToPhysical[static_cast<size_t>(q)] = q;
+    });
+}
+
+int fdd_get_amplitudes(fdd_ctx* ctx, uint64_t first, uint64_t count, double* interleaved) {
+    return guarded([&] {
+        if (ctx == nullptr || interleaved == nullptr) throw std::invalid_argument("null argument");
+        if (!ctx->hasState) throw std::logic_error("no state");
+        if (first + count > ctx->localDim()) throw std::invalid_argument("amplitude range out of bounds");
+        useDevice(ctx);
+        CUDA_TRY(cudaMemcpyAsync(interleaved, ctx->buf[ctx->cur] + first, count * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int fdd_norm2(fdd_ctx* ctx, double* out) {
+    return guarded([&] {
+        if (ctx == nullptr || out == nullptr) throw std::invalid_argument("null argument");
+        if (!ctx->hasState) throw std::logic_error("no state");
+        useDevice(ctx);
+        const uint64_t dim = ctx->localDim();
+        const int grid = std::min(4096, gridFor(ctx, dim, 256));
+        norm2_partial_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->buf[ctx->cur], dim, ctx->dPartial);
+        norm2_final_kernel<<<1, 256, 0, ctx->stream>>>(ctx->dPartial, grid, ctx->dNorm);
+        CUDA_TRY(cudaGetLastError());
+        ctx->launches += 2;
+        CUDA_TRY(cudaMemcpyAsync(out, ctx->dNorm, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int fdd_state_device_ptr(fdd_ctx* ctx, void** ptr) {
+    if (ctx == nullptr || ptr == nullptr) return fail(FDD_ERR_INVALID, "null argument");
+    *ptr = ctx->buf[ctx->cur];
+    return FDD_OK;
+}
+
+int fdd_get_permutation(const fdd_ctx* ctx, int32_t* logical_to_physical) {
+    if (ctx == nullptr || logical_to_physical == nullptr) return fail(FDD_ERR_INVALID, "null argument");
+    std::copy(ctx->logicalToPhysical.begin(), ctx->logicalToPhysical.end(), logical_to_physical);
+    return FDD_OK;
+}
+
+int fdd_canonicalize(fdd_ctx* ctx) {
+    if (ctx == nullptr) return fail(FDD_ERR_INVALID, "ctx is null");
+    for (int q = 0; q < ctx->n; ++q) {
+        if (ctx->logicalToPhysical[static_cast<size_t>(q)] != q) return fail(FDD_ERR_COMM, "qubit remap present but exchange is not built in this revision");
+    }
+    return FDD_OK;
+}
+
+int fdd_last_kernel_ms(fdd_ctx* ctx, float* ms) {
+    if (ctx == nullptr || ms == nullptr) return fail(FDD_ERR_INVALID, "null argument");
+    *ms = ctx->lastMs;
+    return FDD_OK;
+}
+
+int fdd_set_timing(fdd_ctx* ctx, int enabled) {
+    if (ctx == nullptr) return fail(FDD_ERR_INVALID, "ctx is null");
+    ctx->timing = enabled != 0;
+    return FDD_OK;
+}
+
+uint64_t fdd_launch_count(const fdd_ctx* ctx) { return ctx != nullptr ? ctx->launches : 0; }
+
+int fdd_stream(fdd_ctx* ctx, void** stream) {
+    if (ctx == nullptr || stream == nullptr) return fail(FDD_ERR_INVALID, "null argument");
+    *stream = ctx->stream;
+    return FDD_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,486 @@
+// kernels.cuh — sm_100a device code of the FlatDD array phase.
+//
+// Work decomposition shared by both hot kernels.  The amplitude index is split into a
+// SEGMENT (the low S = min(5, n) bits, one warp lane per amplitude, 512 contiguous bytes) and
+// the segment index (the remaining upper bits).  A warp owns TILES of 32 consecutive segments
+// (16 KiB of output) and works in two phases:
+//   phase A  lane j walks the UPPER levels of the decision diagram for segment 32*tile + j
+//            (each lane a different segment), leaving in shared memory what the segment needs;
+//   phase B  the warp sweeps the 32 segments one after the other, lane = amplitude, so every
+//            global access is a full 512-byte coalesced request of 16-byte vectors.
+// The grid is persistent (a multiple of the SM count) and tiles are dealt round-robin to warps
+// so neighbouring warps stream neighbouring DRAM pages.
+//
+// All arithmetic is IEEE fp64.  The conversion kernel uses un-fused multiplies and adds in the
+// reference's order (bit-identical results); DMAVM uses FMAs (tolerance 1e-10).
+#pragma once
+
+#include "gate_compile.hpp"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fddb200 {
+
+constexpr int kWarp = 32;
+constexpr int kMaxPeers = 8;
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ void cmac(double2& acc, double2 a, double2 b) {
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y);
+    acc.y = fma(a.y, b.x, acc.y);
+}
+// un-fused complex multiply in the reference's operation order (include/dd/SwitchPackage.hpp:3616-3619)
+__device__ __forceinline__ double2 cmul_exact(double2 c, double2 w) {
+    return make_double2(__dsub_rn(__dmul_rn(c.x, w.x), __dmul_rn(c.y, w.y)), __dadd_rn(__dmul_rn(c.x, w.y), __dmul_rn(c.y, w.x)));
+}
+__device__ __forceinline__ double2 shfl2(double2 v, int src) {
+    return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+__device__ __forceinline__ void cp_async16(void* smemDst, const void* gmemSrc) {
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smemDst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmemSrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void st_stream(double2* p, double2 v) {
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};\n" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ double2 ld_stream(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// DD -> array conversion
+// ------------------------------------------------------------------------------------------------
+struct alignas(16) VecNode {
+    int32_t child[2]; // successor node or FDD_TERMINAL
+    int32_t level;
+    int32_t pad;
+    double2 w[2];     // exact (0,0) marks a zero edge
+};
+static_assert(sizeof(VecNode) == 48, "VecNode layout");
+
+struct ConvertParams {
+    const VecNode* nodes; // global memory copy of the table
+    int nNodes;
+    int root;
+    double2 rootW;
+    int nQubits;  // all qubits (levels nQubits-1 .. 0)
+    int nLocal;   // qubits held by this shard
+    int segBits;  // S
+    uint32_t rank; // value of the global (top) index bits of this shard
+    uint32_t nSeg;  // local segments
+    uint32_t nTiles;
+    int tableInSmem;
+    double2* out;
+};
+
+// amplitude(i) = w_root * prod_v w(node_v.e[bit_v(i)]), multiplied root first, leaf last
+// (reference getValueByPathPar, include/dd/SwitchPackage.hpp:3605-3634).
+__global__ void __launch_bounds__(256) convert_kernel(const ConvertParams p) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    const VecNode* nodes = p.nodes;
+    if (p.tableInSmem) {
+        VecNode* sn = reinterpret_cast<VecNode*>(smemRaw);
+        const int4* src = reinterpret_cast<const int4*>(p.nodes);
+        int4* dst = reinterpret_cast<int4*>(sn);
+        for (int i = threadIdx.x; i < p.nNodes * 3; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+        nodes = sn;
+    }
+    const int lane = threadIdx.x & 31;
+    const int warpsPerCta = blockDim.x >> 5;
+    const uint32_t warpGlobal = blockIdx.x * warpsPerCta + (threadIdx.x >> 5);
+    const uint32_t warpStride = gridDim.x * warpsPerCta;
+    const int S = p.segBits;
+    const int segLen = 1 << S;
+    const int upperLocalBits = p.nLocal - S; // bits of the local segment index
+
+    for (uint32_t tile = warpGlobal; tile < p.nTiles; tile += warpStride) {
+        // ---- phase A: one segment prefix per lane --------------------------------------------
+        const uint32_t seg = tile * 32u + lane;
+        int node = -1;
+        double2 c = make_double2(1.0, 0.0);
+        bool dead = true;
+        if (seg < p.nSeg) {
+            const uint64_t rowSeg = (static_cast<uint64_t>(p.rank) << upperLocalBits) | seg;
+            dead = false;
+            node = p.root;
+            double2 w = p.rootW;
+            for (int lv = p.nQubits - 1; lv >= S; --lv) {
+                c = cmul_exact(c, w);
+                if (w.x == 0.0 && w.y == 0.0) {
+                    dead = true;
+                    break;
+                }
+                const VecNode& nd = nodes[node];
+                const int b = static_cast<int>((rowSeg >> (lv - S)) & 1ULL);
+                w = nd.w[b];
+                node = nd.child[b];
+            }
+            if (!dead) {
+                // the weight of the edge INTO the level S-1 node is still pending
+                c = cmul_exact(c, w);
+                dead = (w.x == 0.0 && w.y == 0.0);
+            }
+        }
+        // ---- phase B: sweep the segments, lane = amplitude -------------------------------------
+        const int nSegTile = min(32u, p.nSeg - tile * 32u);
+        for (int j = 0; j < nSegTile; ++j) {
+            const int nodeJ = __shfl_sync(0xffffffffu, node, j);
+            const double2 cJ = shfl2(c, j);
+            const bool deadJ = __shfl_sync(0xffffffffu, static_cast<int>(dead), j) != 0;
+            if (lane < segLen) {
+                double2 a = cJ;
+                bool z = deadJ;
+                int u = nodeJ;
+                if (!z) {
+                    for (int lv = S - 1; lv >= 0; --lv) {
+                        const VecNode& nd = nodes[u];
+                        const int b = (lane >> lv) & 1;
+                        const double2 w = nd.w[b];
+                        a = cmul_exact(a, w);
+                        if (w.x == 0.0 && w.y == 0.0) {
+                            z = true;
+                            break;
+                        }
+                        u = nd.child[b];
+                    }
+                }
+                if (z) a = make_double2(0.0, 0.0);
+                st_stream(p.out + ((static_cast<uint64_t>(tile) * 32u + j) << S) + lane, a);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// DMAVM walk kernel
+// ------------------------------------------------------------------------------------------------
+struct WalkParams {
+    const double2* y;                 // source state (this shard)
+    const double2* peerY[kMaxPeers];  // source shards of all ranks (peerY[rank] == y); multi-GPU only
+    double2* z;                       // destination state (this shard)
+    const UpperNode* upper;
+    int nUpper;
+    const double2* subW;              // [nSub][kMax][32]
+    const uint8_t* subCol;            // [nSub][kMax][32]
+    const int32_t* subK;              // [nSub]
+    const uint8_t* subFlags;          // [nSub]
+    int nSub;
+    int kMax;
+    int root;                         // encoded like UpperNode::child
+    double2 rootW;
+    int nLocal;
+    int segBits;
+    int maxPaths;
+    int stackCap;
+    uint32_t rank;
+    int worldBits;
+    uint32_t nSeg;
+    uint32_t nTiles;
+    int tablesInSmem;
+    int prefetch;                     // ring depth D (variant 1)
+};
+
+// Bytes of shared memory one warp needs.
+__host__ __device__ inline size_t walkWarpSmem(int maxPaths, int stackCap, int prefetch) {
+    return static_cast<size_t>(maxPaths + stackCap) * 32 * 24 + static_cast<size_t>(prefetch) * 512;
+}
+__host__ __device__ inline size_t walkTableSmem(int nUpper, int nSub, int kMax) {
+    size_t b = static_cast<size_t>(nUpper) * sizeof(UpperNode);
+    b += static_cast<size_t>(nSub) * kMax * 32 * 16; // subW
+    b += static_cast<size_t>(nSub) * kMax * 32;      // subCol
+    b += static_cast<size_t>(nSub) * 4;              // subK
+    b += static_cast<size_t>(nSub);                  // subFlags
+    return (b + 15) & ~static_cast<size_t>(15);
+}
+
+// z[r] = sum_c M[r][c] y[c]   (reference DDArrMultiplyIP, include/dd/SwitchPackage.hpp:1897-2261)
+//
+// VARIANT 0: source segments are loaded straight into registers (one LDG.128 per lane) and
+//            permuted with warp shuffles.
+// VARIANT 1: source segments are staged through a per-warp ring of `prefetch` 512-byte slots
+//            in shared memory filled by cp.async, so several DRAM requests per warp are in flight
+//            while earlier segments are consumed; the permutation is a shared-memory gather.
+template <int VARIANT> __global__ void __launch_bounds__(512) dmavm_walk_kernel(const WalkParams p) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    unsigned char* cursor = smemRaw;
+    const UpperNode* upper = p.upper;
+    const double2* subW = p.subW;
+    const uint8_t* subCol = p.subCol;
+    const int32_t* subK = p.subK;
+    const uint8_t* subFlags = p.subFlags;
+    if (p.tablesInSmem) {
+        // stage the gate tables (all sizes are multiples of 4 bytes except the byte tables)
+        UpperNode* su = reinterpret_cast<UpperNode*>(cursor);
+        cursor += static_cast<size_t>(p.nUpper) * sizeof(UpperNode);
+        double2* sw = reinterpret_cast<double2*>(cursor);
+        const int nEnt = p.nSub * p.kMax * 32;
+        cursor += static_cast<size_t>(nEnt) * 16;
+        int32_t* sk = reinterpret_cast<int32_t*>(cursor);
+        cursor += static_cast<size_t>(p.nSub) * 4;
+        uint8_t* sc = cursor;
+        cursor += nEnt;
+        uint8_t* sf = cursor;
+        cursor += p.nSub;
+        {
+            const int4* src = reinterpret_cast<const int4*>(p.upper);
+            int4* dst = reinterpret_cast<int4*>(su);
+            for (int i = threadIdx.x; i < p.nUpper * 6; i += blockDim.x) dst[i] = src[i];
+        }
+        for (int i = threadIdx.x; i < nEnt; i += blockDim.x) {
+            sw[i] = p.subW[i];
+            sc[i] = p.subCol[i];
+        }
+        for (int i = threadIdx.x; i < p.nSub; i += blockDim.x) {
+            sk[i] = p.subK[i];
+            sf[i] = p.subFlags[i];
+        }
+        __syncthreads();
+        upper = su;
+        subW = sw;
+        subCol = sc;
+        subK = sk;
+        subFlags = sf;
+        cursor = smemRaw + walkTableSmem(p.nUpper, p.nSub, p.kMax);
+    }
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warpsPerCta = blockDim.x >> 5;
+    const int D = p.prefetch;
+    unsigned char* mine = cursor + static_cast<size_t>(warp) * walkWarpSmem(p.maxPaths, p.stackCap, VARIANT == 1 ? D : 0);
+    // per-warp arrays, [slot][lane]
+    const int nSlots = p.maxPaths + p.stackCap;
+    double2* eW = reinterpret_cast<double2*>(mine);                               // [nSlots][32]
+    int32_t* eCode = reinterpret_cast<int32_t*>(mine + static_cast<size_t>(nSlots) * 32 * 16); // [nSlots][32]
+    uint32_t* eCol = reinterpret_cast<uint32_t*>(mine + static_cast<size_t>(nSlots) * 32 * 20); // [nSlots][32]
+    double2* ring = reinterpret_cast<double2*>(mine + static_cast<size_t>(nSlots) * 32 * 24);   // [D][32]
+    // entries occupy slots [0, maxPaths), the DFS stack slots [maxPaths, nSlots)
+    const int stackBase = p.maxPaths;
+
+    const uint32_t warpGlobal = blockIdx.x * warpsPerCta + warp;
+    const uint32_t warpStride = gridDim.x * warpsPerCta;
+    const int S = p.segBits;
+    const int segLen = 1 << S;
+    const int upperLocalBits = p.nLocal - S;
+    const uint32_t localSegMask = (upperLocalBits >= 32) ? 0xffffffffu : ((1u << upperLocalBits) - 1u);
+
+    for (uint32_t tile = warpGlobal; tile < p.nTiles; tile += warpStride) {
+        // =================== phase A: upper walk, one segment per lane ===========================
+        const uint32_t seg = tile * 32u + lane;
+        int cnt = 0;
+        if (seg < p.nSeg && p.root != FDD_TERMINAL) {
+            const uint32_t rowSeg = (p.rank << upperLocalBits) | seg; // segment index incl. global bits
+            int sp = 0;
+            int code = p.root;
+            double2 w = p.rootW;
+            uint32_t col = 0;
+            for (;;) {
+                while (code >= 0) {
+                    const UpperNode& nd = upper[code];
+                    const int sh = nd.level - S;
+                    const int rb = static_cast<int>((rowSeg >> sh) & 1u);
+                    const int2 ch = *reinterpret_cast<const int2*>(&nd.child[2 * rb]);
+                    const double2* nw = reinterpret_cast<const double2*>(nd.w) + 2 * rb;
+                    if (ch.x != FDD_TERMINAL) {
+                        if (ch.y != FDD_TERMINAL) {
+                            const int slot = (stackBase + sp) * 32 + lane;
+                            eW[slot] = cmul(w, nw[1]);
+                            eCode[slot] = ch.y;
+                            eCol[slot] = col | (1u << sh);
+                            ++sp;
+                        }
+                        w = cmul(w, nw[0]);
+                        code = ch.x;
+                    } else if (ch.y != FDD_TERMINAL) {
+                        w = cmul(w, nw[1]);
+                        col |= (1u << sh);
+                        code = ch.y;
+                    } else {
+                        code = FDD_TERMINAL; // dead end: this row has no entry below this node
+                    }
+                }
+                if (code <= -2) {
+                    const int slot = cnt * 32 + lane;
+                    eW[slot] = w;
+                    eCode[slot] = -2 - code; // decodeSub
+                    eCol[slot] = col;
+                    ++cnt;
+                }
+                if (sp == 0) break;
+                --sp;
+                const int slot = (stackBase + sp) * 32 + lane;
+                w = eW[slot];
+                code = eCode[slot];
+                col = eCol[slot];
+            }
+        }
+        __syncwarp();
+
+        // =================== phase B: sweep the segments, lane = row ================================
+        const int nSegTile = static_cast<int>(min(32u, p.nSeg - tile * 32u));
+        double2* zTile = p.z + ((static_cast<uint64_t>(tile) * 32u) << S);
+
+        if (VARIANT == 0) {
+            for (int j = 0; j < nSegTile; ++j) {
+                const int cj = __shfl_sync(0xffffffffu, cnt, j);
+                double2 acc = make_double2(0.0, 0.0);
+                for (int i = 0; i < cj; ++i) {
+                    const int slot = i * 32 + j;
+                    const double2 w = eW[slot];
+                    const int sub = eCode[slot];
+                    const uint32_t col = eCol[slot];
+                    const double2* src = (p.worldBits == 0) ? p.y : p.peerY[col >> upperLocalBits];
+                    double2 own = make_double2(0.0, 0.0);
+                    if (lane < segLen) own = ld_stream(src + ((static_cast<uint64_t>(col & localSegMask)) << S) + lane);
+                    const int flags = subFlags[sub];
+                    if (flags & SUB_IDENTITY) {
+                        cmac(acc, w, own);
+                    } else if (flags & SUB_DIAGONAL) {
+                        cmac(acc, cmul(w, subW[sub * p.kMax * 32 + lane]), own);
+                    } else {
+                        const int kk = subK[sub];
+                        for (int k = 0; k < kk; ++k) {
+                            const int at = (sub * p.kMax + k) * 32 + lane;
+                            const double2 yv = shfl2(own, subCol[at]);
+                            cmac(acc, cmul(w, subW[at]), yv);
+                        }
+                    }
+                }
+                if (lane < segLen) st_stream(zTile + (static_cast<uint64_t>(j) << S) + lane, acc);
+            }
+        } else {
+            // two cursors over the tile's (segment, entry) pairs: `pj,pi` issues copies, `j,i` consumes
+            int pj = 0, pi = 0;
+            int pcnt = __shfl_sync(0xffffffffu, cnt, 0);
+            int issued = 0;
+            auto issueNext = [&]() {
+                while (pj < nSegTile && pi >= pcnt) { // skip exhausted / empty segments
+                    ++pj;
+                    pi = 0;
+                    pcnt = __shfl_sync(0xffffffffu, cnt, pj & 31);
+                }
+                if (pj < nSegTile) {
+                    const int slot = pi * 32 + pj;
+                    const uint32_t col = eCol[slot];
+                    const double2* src = (p.worldBits == 0) ? p.y : p.peerY[col >> upperLocalBits];
+                    if (lane < segLen) {
+                        cp_async16(ring + (issued % D) * 32 + lane, src + ((static_cast<uint64_t>(col & localSegMask)) << S) + lane);
+                    }
+                    ++pi;
+                    ++issued;
+                }
+                cp_async_commit(); // one group per call, possibly empty, keeps the group arithmetic uniform
+            };
+            for (int q = 0; q < D; ++q) issueNext();
+            int consumed = 0;
+            for (int j = 0; j < nSegTile; ++j) {
+                const int cj = __shfl_sync(0xffffffffu, cnt, j);
+                double2 acc = make_double2(0.0, 0.0);
+                for (int i = 0; i < cj; ++i) {
+                    // groups complete in order: leaving D-1 pending means the oldest (ours) has landed
+                    switch (D) {
+                        case 1: cp_async_wait<0>(); break;
+                        case 2: cp_async_wait<1>(); break;
+                        case 4: cp_async_wait<3>(); break;
+                        case 8: cp_async_wait<7>(); break;
+                        default: cp_async_wait<15>(); break;
+                    }
+                    __syncwarp();
+                    const double2* slotData = ring + (consumed % D) * 32;
+                    const int slot = i * 32 + j;
+                    const double2 w = eW[slot];
+                    const int sub = eCode[slot];
+                    const int flags = subFlags[sub];
+                    if (flags & SUB_IDENTITY) {
+                        cmac(acc, w, slotData[lane]);
+                    } else if (flags & SUB_DIAGONAL) {
+                        cmac(acc, cmul(w, subW[sub * p.kMax * 32 + lane]), slotData[lane]);
+                    } else {
+                        const int kk = subK[sub];
+                        for (int k = 0; k < kk; ++k) {
+                            const int at = (sub * p.kMax + k) * 32 + lane;
+                            cmac(acc, cmul(w, subW[at]), slotData[subCol[at]]);
+                        }
+                    }
+                    ++consumed;
+                    __syncwarp(); // every lane is done with the slot before it is refilled
+                    issueNext();
+                }
+                if (lane < segLen) st_stream(zTile + (static_cast<uint64_t>(j) << S) + lane, acc);
+            }
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// utility kernels
+// ------------------------------------------------------------------------------------------------
+// interleaved complex -> two planar arrays (the reference's state_real / state_imag layout)
+__global__ void deinterleave_kernel(const double2* __restrict__ in, double* __restrict__ re, double* __restrict__ im, uint64_t n) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double2 v = in[i];
+        re[i] = v.x;
+        im[i] = v.y;
+    }
+}
+__global__ void interleave_kernel(const double* __restrict__ re, const double* __restrict__ im, double2* __restrict__ out, uint64_t n) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        out[i] = make_double2(re[i], im[i]);
+    }
+}
+__global__ void zero_state_kernel(double2* out, uint64_t n, int setOne) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        out[i] = make_double2((i == 0 && setOne) ? 1.0 : 0.0, 0.0);
+    }
+}
+// sum |amp|^2: per-block partial sums in fixed order, final pass on one block (deterministic)
+__global__ void norm2_partial_kernel(const double2* __restrict__ in, uint64_t n, double* __restrict__ partial) {
+    __shared__ double sh[32];
+    double s = 0.0;
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double2 v = in[i];
+        s = fma(v.x, v.x, s);
+        s = fma(v.y, v.y, s);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    }
+}
+__global__ void norm2_final_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+    __shared__ double sh[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) *out = s;
+    }
+}
+
+} // namespace fddb200

@@ -1,0 +1,148 @@
+// array_backend.hpp — what the simulator driver talks to once the state has left the DD.
+//
+// Three implementations:
+//   * GpuArrayBackend   — the product: forwards to the C-ABI in include/flatdd_b200.h
+//                         (sm_100a kernels).  Throws std::runtime_error on any failure; there
+//                         is no CPU fallback.
+//   * TraceRecorder     — writes every flat table that crosses the boundary to a binary trace
+//                         (used to ship a circuit's array phase to a box that has no
+//                         reference tree, and to generate golden fixtures).
+//   * TeeBackend        — fan-out to several backends.
+// (The CPU backend that drives the *reference's own* DDArrMultiplyIP lives in
+//  oracle/ref_dump.cpp: it is test infrastructure, not product.)
+#pragma once
+
+#include "flatdd_b200.h"
+#include "flatten.hpp"
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace fddb200 {
+
+class ArrayBackend {
+public:
+    virtual ~ArrayBackend() = default;
+    // DD -> array (reference: getVectorFromDDSwitch1 / getVectorFromDD)
+    virtual void convert(const FlatVecDD& dd) = 0;
+    // one DMAVM (reference: DDArrMultiplyIP / DDArrMultiplyOP); `nOriginalGates` = how many
+    // circuit operations were fused into this matrix (bookkeeping only)
+    virtual void apply(const FlatMatDD& gate, int nOriginalGates) = 0;
+    // copy the current state into SoA arrays of 2^n doubles (reference: getVector)
+    virtual void getState(double* real, double* imag) = 0;
+    virtual void synchronize() {}
+};
+
+inline void fddCheck(int rc, const char* what) {
+    if (rc != FDD_OK) {
+        throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " + fdd_last_error());
+    }
+}
+
+class GpuArrayBackend final : public ArrayBackend {
+public:
+    GpuArrayBackend(int nQubits, int device = 0) { fddCheck(fdd_create(nQubits, device, &ctx_), "fdd_create"); }
+    GpuArrayBackend(const GpuArrayBackend&) = delete;
+    GpuArrayBackend& operator=(const GpuArrayBackend&) = delete;
+    ~GpuArrayBackend() override {
+        if (ctx_ != nullptr) {
+            fdd_destroy(ctx_);
+        }
+    }
+    void convert(const FlatVecDD& dd) override {
+        const fdd_vecdd v = view(dd);
+        fddCheck(fdd_convert(ctx_, &v), "fdd_convert");
+    }
+    void apply(const FlatMatDD& gate, int /*nOriginalGates*/) override {
+        const fdd_matdd m = view(gate);
+        fddCheck(fdd_apply(ctx_, &m), "fdd_apply");
+    }
+    void getState(double* real, double* imag) override { fddCheck(fdd_get_state(ctx_, real, imag), "fdd_get_state"); }
+    void synchronize() override { fddCheck(fdd_synchronize(ctx_), "fdd_synchronize"); }
+    [[nodiscard]] fdd_ctx* ctx() const { return ctx_; }
+
+private:
+    fdd_ctx* ctx_ = nullptr;
+};
+
+// Binary trace, little endian:
+//   char[8] "FDDTRC01"; int32 n_qubits; int32 n_records (patched on close);
+//   records: int32 kind (1 = vector DD to convert, 2 = matrix DD to apply), int32 n_nodes,
+//            int32 root, int32 n_original_gates, double root_weight[2],
+//            int32 level[n_nodes], int32 child[R*n_nodes], double weight[2*R*n_nodes]   (R = 2 or 4)
+class TraceRecorder final : public ArrayBackend {
+public:
+    TraceRecorder(const std::string& path, int nQubits) : file_(std::fopen(path.c_str(), "wb")) {
+        if (file_ == nullptr) {
+            throw std::runtime_error("TraceRecorder: cannot open " + path);
+        }
+        const char magic[8] = {'F', 'D', 'D', 'T', 'R', 'C', '0', '1'};
+        put(magic, sizeof magic);
+        const int32_t n = nQubits;
+        put(&n, sizeof n);
+        put(&records_, sizeof records_);
+    }
+    TraceRecorder(const TraceRecorder&) = delete;
+    TraceRecorder& operator=(const TraceRecorder&) = delete;
+    ~TraceRecorder() override { close(); }
+    void convert(const FlatVecDD& dd) override { record<2>(1, dd, 0); }
+    void apply(const FlatMatDD& gate, int nOriginalGates) override { record<4>(2, gate, nOriginalGates); }
+    void getState(double*, double*) override { throw std::runtime_error("TraceRecorder holds no state"); }
+    void close() {
+        if (file_ != nullptr) {
+            std::fseek(file_, 12, SEEK_SET);
+            put(&records_, sizeof records_);
+            std::fclose(file_);
+            file_ = nullptr;
+        }
+    }
+    [[nodiscard]] int32_t records() const { return records_; }
+
+private:
+    void put(const void* p, std::size_t bytes) {
+        if (bytes != 0 && std::fwrite(p, 1, bytes, file_) != bytes) {
+            throw std::runtime_error("TraceRecorder: short write");
+        }
+    }
+    template <int R> void record(int32_t kind, const FlatDD<R>& dd, int32_t nOriginal) {
+        const int32_t head[4] = {kind, dd.nNodes(), dd.root, nOriginal};
+        put(head, sizeof head);
+        put(dd.root_weight, sizeof dd.root_weight);
+        put(dd.level.data(), dd.level.size() * sizeof(int32_t));
+        put(dd.child.data(), dd.child.size() * sizeof(int32_t));
+        put(dd.weight.data(), dd.weight.size() * sizeof(double));
+        ++records_;
+    }
+    std::FILE* file_;
+    int32_t records_ = 0;
+};
+
+class TeeBackend final : public ArrayBackend {
+public:
+    explicit TeeBackend(std::vector<ArrayBackend*> sinks) : sinks_(std::move(sinks)) {}
+    void convert(const FlatVecDD& dd) override {
+        for (auto* s : sinks_) {
+            s->convert(dd);
+        }
+    }
+    void apply(const FlatMatDD& gate, int nOriginalGates) override {
+        for (auto* s : sinks_) {
+            s->apply(gate, nOriginalGates);
+        }
+    }
+    // the first sink owns the state
+    void getState(double* real, double* imag) override { sinks_.front()->getState(real, imag); }
+    void synchronize() override {
+        for (auto* s : sinks_) {
+            s->synchronize();
+        }
+    }
+
+private:
+    std::vector<ArrayBackend*> sinks_;
+};
+
+} // namespace fddb200

@@ -1,0 +1,505 @@
+// gpu_switch_simulator.hpp — host driver with the public surface of the reference's
+// SwitchSimulator (reference include/SwitchSimulator.hpp:23-419, src/SwitchSimulator.cpp:15-590),
+// whose array phase runs behind an ArrayBackend (the sm_100a C-ABI library in production).
+//
+// What is kept from the reference ("R" rows):
+//   * DD phase on the host DD package: rootEdge = multiply(getDD(op), rootEdge) per gate
+//     (fuse == 0, src/SwitchSimulator.cpp:135-141) or per group of 6 pre-multiplied gates
+//     (fuse >= 1, :229-248);
+//   * the switch rule: EMA_0 = n; after every applied gate/group s = size(rootEdge);
+//     switch iff EMA > 0 && EMA * threshold < s, tested with the old EMA, then
+//     EMA = beta * EMA + (1 - beta) * s (:97, 163-165, 181, 250-253, 379);
+//   * fuse == 1: the greedy DMAVM-aware schedule with the reference's own cost functions
+//     (:271-340) and fuse == 2: the 6-gate op-count schedule (:341-372); both stop at the first
+//     non-unitary operation; measurements / resets / barriers are skipped, never sampled;
+//   * the no-switch ablation enable_switch == false (:415-587);
+//   * public knobs threshold / beta / n_thread_exp / fuse / enable_cache / ddsim_convert /
+//     enable_switch and results switched / switchTime / timeRecord1 / timeRecord2 / rootEdge.
+// What is new:
+//   * fuse == 3: the same greedy control flow driven by the GPU cost model (fdd_cost_gpu: one
+//     launch costs max(HBM time, fp64 time) and a bound on the DD size), see DESIGN.md;
+//   * identity gates (barriers) are detected and not launched; no memsets; no scratch arrays;
+//   * the state lives on the device; getVector materialises host arrays lazily.
+//
+// Template parameter Package is the host DD package type, e.g. dd::SwitchPackage<dd::DDPackageConfig>;
+// Qc is the circuit type (qc::QuantumComputation).  DdOps supplies getDD(op, dd).
+#pragma once
+
+#include "array_backend.hpp"
+#include "flatten.hpp"
+
+#include <chrono>
+#include <cmath>
+#include <cstddef>
+#include <iostream>
+#include <memory>
+#include <stdexcept>
+#include <unordered_map>
+#include <vector>
+
+namespace fddb200 {
+
+struct FusionPolicy {
+    double hbmGBs = 6500.0;      // MEASURED_PEAKS.json hbm_gbs
+    double fp64GFlops = 30000.0; // sustained fp64 FMA rate assumed by the cost model
+    int maxNodes = 4096;         // bound on the flat table of a fused gate
+};
+
+template <class Package, class Qc, class DdOps, class WeightTraits> class GpuSwitchSimulator {
+public:
+    using VEdge = decltype(std::declval<Package&>().makeZeroState(1));
+    using MEdge = decltype(std::declval<Package&>().makeIdent(1));
+    using fp = double;
+
+    GpuSwitchSimulator(std::unique_ptr<Qc>&& circuit, ArrayBackend* backend_) : qc(std::move(circuit)), backend(backend_) {
+        dd->resize(qc->getNqubits());
+    }
+
+    // ---- reference surface ------------------------------------------------------------------
+    void simulate() {
+        dd->n_thread_exp = n_thread_exp;
+        bool otherNonUnitary = false;
+        bool sawMeasure = false;
+        bool measuresTrail = true;
+        for (auto& op : *qc) {
+            if (op->isClassicControlledOperation() ||
+                (op->isNonUnitaryOperation() && !DdOps::isMeasure(*op) && !DdOps::isBarrier(*op))) {
+                otherNonUnitary = true;
+            }
+            if (DdOps::isMeasure(*op)) {
+                sawMeasure = true;
+            }
+            if (sawMeasure && op->isUnitary()) {
+                measuresTrail = false;
+            }
+        }
+        if (!otherNonUnitary && !sawMeasure) {
+            run(false);
+        } else if (!otherNonUnitary && measuresTrail) {
+            run(true);
+        }
+        // anything else is silently not simulated, like the reference (src/SwitchSimulator.cpp:62)
+    }
+
+    // Borrowed pointers to host SoA copies of the current state (reference getVector, :55-63).
+    void getVector(fp*& realVec, fp*& imagVec) {
+        if (getNumberOfQubits() >= 60) {
+            throw std::range_error("getVector only supports less than 60 qubits.");
+        }
+        materialise();
+        realVec = hostReal.data();
+        imagVec = hostImag.data();
+    }
+
+    // Convert the current rootEdge on the device (reference getVectorFromDD / getVectorFromDDSwitch1).
+    void getVectorFromDD(int /*idx*/ = 0) {
+        backend->convert(flatten<2, VEdge, WeightTraits>(rootEdge, static_cast<int>(getNumberOfQubits())));
+        hostValid = false;
+        onDevice = true;
+    }
+
+    [[nodiscard]] std::vector<fp> getTimeRecord1() const { return timeRecord1; }
+    [[nodiscard]] std::vector<fp> getTimeRecord2() const { return timeRecord2; }
+    [[nodiscard]] fp getSwitchTime() const { return switchTime; }
+    [[nodiscard]] std::size_t getNumberOfQubits() const { return qc->getNqubits(); }
+    [[nodiscard]] std::size_t getNumberOfOps() const { return qc->getNops(); }
+    [[nodiscard]] std::string getName() const { return qc->getName(); }
+
+    std::unique_ptr<Package> dd = std::make_unique<Package>();
+    VEdge rootEdge{};
+    std::vector<fp> timeRecord1;
+    std::vector<fp> timeRecord2;
+    fp switchTime = 0.0; // the reference leaves this uninitialised when no switch happens
+    unsigned int n_thread_exp = 0;
+    bool switched = false;
+    bool ddsim_convert = false; // accepted for CLI parity; both conversions are the same kernel here
+    bool enable_switch = true;
+    unsigned int fuse = 0;
+    bool enable_cache = true;
+    double EMA_v = 0;
+    double beta = 0.9;
+    double threshold = 3.5;
+
+    // ---- additions ---------------------------------------------------------------------------
+    FusionPolicy policy{};
+    long switchedAtOp = -1;        // index printed as "Switching at instr."
+    std::size_t unitaryOps = 0;    // unitary operations seen (incl. barriers)
+    std::size_t arrayPhaseOps = 0; // circuit operations executed in the array phase
+    std::size_t launches = 0;      // DMAVM launches issued
+    double gateMergingTime = 0.0;
+    double arrayPhaseTime = 0.0;
+    bool verbose = true;
+
+private:
+    using Clock = std::chrono::steady_clock;
+    static double since(Clock::time_point t0) { return std::chrono::duration<double>(Clock::now() - t0).count(); }
+
+    [[nodiscard]] int nq() const { return static_cast<int>(qc->getNqubits()); }
+
+    // true for operations the per-gate loop skips; throws for unsupported ones
+    // (src/SwitchSimulator.cpp:103-130)
+    bool skipped(const typename Qc::iterator::value_type& op, bool ignoreNonUnitaries) {
+        if (op->isNonUnitaryOperation()) {
+            if (ignoreNonUnitaries || DdOps::isMeasure(*op) || DdOps::isReset(*op) || DdOps::isBarrier(*op)) {
+                return true;
+            }
+            throw std::runtime_error("Unsupported non-unitary functionality.");
+        }
+        if (op->isClassicControlledOperation()) {
+            throw std::runtime_error("Unsupported classical control functionality.");
+        }
+        return false;
+    }
+
+    bool emaSwitchTest(double ddSize) {
+        const double next = EMA_v * beta + (1 - beta) * ddSize;
+        const bool fire = !switched && EMA_v > 0 && EMA_v * threshold < ddSize;
+        pendingEma = next;
+        return fire;
+    }
+
+    void doSwitch(std::size_t opNum) {
+        if (verbose) {
+            std::cout << "Switching from DDSIM to FLATDD!!" << std::endl;
+            std::cout << "Switching at instr.  " << opNum << std::endl;
+        }
+        const auto t0 = Clock::now();
+        switched = true;
+        switchedAtOp = static_cast<long>(opNum);
+        getVectorFromDD();
+        backend->synchronize();
+        switchTime = since(t0);
+    }
+
+    void launch(const MEdge& gate, int nOriginal) {
+        const auto flat = flatten<4, MEdge, WeightTraits>(gate, nq());
+        backend->apply(flat, nOriginal);
+        ++launches;
+        arrayPhaseOps += static_cast<std::size_t>(nOriginal);
+        hostValid = false;
+    }
+
+    void multiplyIntoRoot(const MEdge& gate) {
+        auto next = dd->multiply(gate, rootEdge);
+        dd->incRef(next);
+        dd->decRef(rootEdge);
+        rootEdge = next;
+    }
+
+    void run(bool ignoreNonUnitaries) {
+        const auto n = qc->getNqubits();
+        rootEdge = dd->makeZeroState(n);
+        dd->incRef(rootEdge);
+        EMA_v = static_cast<double>(n);
+        if (!enable_switch) {
+            runAllArray(ignoreNonUnitaries);
+        } else if (fuse == 0) {
+            runPerGate(ignoreNonUnitaries);
+        } else {
+            runFused(ignoreNonUnitaries);
+        }
+        backend->synchronize();
+    }
+
+    // fuse == 0 (src/SwitchSimulator.cpp:99-188)
+    void runPerGate(bool ignoreNonUnitaries) {
+        std::size_t opNum = 0;
+        Clock::time_point arrayStart{};
+        for (auto& op : *qc) {
+            if (skipped(op, ignoreNonUnitaries)) {
+                continue;
+            }
+            if (verbose && opNum % 100 == 0) {
+                std::cout << "[Instruction Count]  " << opNum << std::endl;
+            }
+            const auto t0 = Clock::now();
+            auto gate = DdOps::getDD(op.get(), dd);
+            if (!switched) {
+                multiplyIntoRoot(gate);
+            } else {
+                launch(gate, 1);
+            }
+            dd->garbageCollect();
+            (switched ? timeRecord2 : timeRecord1).push_back(since(t0));
+            if (!switched) {
+                const double ddSize = static_cast<double>(dd->size(rootEdge));
+                if (emaSwitchTest(ddSize)) {
+                    doSwitch(opNum);
+                    arrayStart = Clock::now();
+                }
+                EMA_v = pendingEma;
+            }
+            ++opNum;
+        }
+        unitaryOps = opNum;
+        if (switched) {
+            backend->synchronize();
+            arrayPhaseTime = since(arrayStart);
+        }
+    }
+
+    struct Schedule {
+        std::vector<MEdge> gates;
+        std::vector<int> originals; // circuit operations per fused gate
+        std::vector<bool> useCache; // the reference's in_or_out flag (statistics only)
+    };
+
+    // cost of one gate under the active policy
+    struct Cost {
+        std::size_t value = 0;
+        std::size_t ip = 0;
+        bool cache = false;
+    };
+
+    Cost referenceCost(const MEdge& g, std::unordered_map<decltype(g.p), std::size_t>& macMap, std::size_t nDim) {
+        Cost c;
+        c.ip = dd->DMAVMACStatIP(g, macMap, nDim, n_thread_exp);
+        const std::size_t op1 = dd->DMAVMACStatOP1(g, macMap, nDim, n_thread_exp);
+        c.cache = !(c.ip < op1);
+        c.value = c.cache ? op1 : c.ip;
+        return c;
+    }
+
+    Cost gpuCost(const MEdge& g) {
+        Cost c;
+        const auto flat = flatten<4, MEdge, WeightTraits>(g, nq());
+        if (flat.nNodes() > policy.maxNodes) {
+            c.value = c.ip = static_cast<std::size_t>(-1) / 4;
+            return c;
+        }
+        const fdd_matdd m = view(flat);
+        double ns = 0.0;
+        const int rc = fdd_cost_gpu(&m, policy.hbmGBs, policy.fp64GFlops, &ns);
+        if (rc == FDD_ERR_TOO_DENSE) {
+            c.value = c.ip = static_cast<std::size_t>(-1) / 4;
+            return c;
+        }
+        fddCheck(rc, "fdd_cost_gpu");
+        c.value = c.ip = static_cast<std::size_t>(ns);
+        return c;
+    }
+
+    // Greedy schedule over ops[first..] up to the first non-unitary operation.
+    // Control flow of src/SwitchSimulator.cpp:271-340 (fuse 1), :341-372 (fuse 2); fuse 3 swaps the cost.
+    Schedule buildSchedule(std::size_t first) {
+        Schedule s;
+        const std::size_t nDim = std::size_t{1} << qc->getNqubits();
+        const auto& ops = qc->ops;
+        auto current = dd->makeIdent(qc->getNqubits());
+        int currentCount = 0;
+        if (fuse == 2) {
+            if (verbose) {
+                std::cout << "Using op-count-based merge from DATE '19... " << std::endl;
+            }
+            std::size_t merged = 0;
+            for (std::size_t k = first; k < ops.size() && !ops[k]->isNonUnitaryOperation(); ++k) {
+                auto next = DdOps::getDD(ops[k].get(), dd);
+                auto candidate = dd->multiply(next, current);
+                ++merged;
+                if (merged > 5) {
+                    s.gates.push_back(current);
+                    s.originals.push_back(currentCount);
+                    s.useCache.push_back(false);
+                    current = next;
+                    currentCount = 1;
+                    merged = 0;
+                } else {
+                    current = candidate;
+                    ++currentCount;
+                }
+            }
+            s.gates.push_back(current);
+            s.originals.push_back(currentCount);
+            s.useCache.push_back(false);
+            return s;
+        }
+        if (verbose) {
+            std::cout << (fuse == 1 ? "Using greedy merge... " : "Using GPU-cost greedy merge... ") << std::endl;
+        }
+        std::unordered_map<decltype(current.p), std::size_t> macMap;
+        Cost held; // cost of `current`
+        std::size_t totalComp = 0;
+        std::size_t savedComp = 0;
+        for (std::size_t k = first; k < ops.size() && !ops[k]->isNonUnitaryOperation(); ++k) {
+            auto next = DdOps::getDD(ops[k].get(), dd);
+            const Cost nextCost = fuse == 1 ? referenceCost(next, macMap, nDim) : gpuCost(next);
+            auto candidate = dd->multiply(next, current);
+            const Cost mergedCost = fuse == 1 ? referenceCost(candidate, macMap, nDim) : gpuCost(candidate);
+            const bool lastOp = k == ops.size() - 1 || ops[k + 1]->isNonUnitaryOperation();
+            if (held.value + nextCost.value < mergedCost.value || lastOp) {
+                s.gates.push_back(current);
+                s.originals.push_back(currentCount);
+                s.useCache.push_back(held.cache);
+                totalComp += held.ip;
+                savedComp += held.ip - held.value;
+                held = nextCost;
+                current = next;
+                currentCount = 1;
+                macMap.clear();
+            } else {
+                current = candidate;
+                ++currentCount;
+                held = mergedCost;
+            }
+        }
+        s.gates.push_back(current);
+        s.originals.push_back(currentCount);
+        s.useCache.push_back(false);
+        totalComp += held.ip;
+        if (verbose) {
+            std::cout << "Cost: " << totalComp - savedComp << std::endl;
+            std::cout << "Saved cost %: "
+                      << 100 * static_cast<double>(savedComp) / static_cast<double>(totalComp == 0 ? 1 : totalComp) << "%"
+                      << std::endl;
+        }
+        return s;
+    }
+
+    void execute(const Schedule& s) {
+        if (verbose) {
+            std::cout << "Merged Gate Number: " << s.gates.size() << "\n";
+        }
+        const auto t0 = Clock::now();
+        for (std::size_t i = 0; i < s.gates.size(); ++i) {
+            const auto tg = Clock::now();
+            if (!isIdentity(s.gates[i])) {
+                launch(s.gates[i], s.originals[i]);
+            } else {
+                arrayPhaseOps += static_cast<std::size_t>(s.originals[i]);
+            }
+            timeRecord2.push_back(since(tg));
+        }
+        backend->synchronize();
+        arrayPhaseTime = since(t0);
+        if (verbose) {
+            std::cout << "runtime after conversion: " << arrayPhaseTime << std::endl;
+        }
+    }
+
+    // fuse >= 1 (src/SwitchSimulator.cpp:189-413)
+    void runFused(bool ignoreNonUnitaries) {
+        std::size_t opNum = 0;
+        int mergeNum = 0;
+        auto group = dd->makeIdent(qc->getNqubits());
+        const auto& ops = qc->ops;
+        Schedule schedule;
+        for (auto& op : *qc) {
+            if (skipped(op, ignoreNonUnitaries)) {
+                continue;
+            }
+            ++mergeNum;
+            auto gate = DdOps::getDD(op.get(), dd);
+            group = dd->multiply(gate, group);
+            // the reference indexes qc->ops with the count of unitary operations (:234-235)
+            const bool flush = (!switched && mergeNum > 5) || opNum == ops.size() - 1 ||
+                               (opNum < ops.size() - 1 && ops[opNum + 1]->isNonUnitaryOperation());
+            if (flush) {
+                const auto t0 = Clock::now();
+                multiplyIntoRoot(group);
+                mergeNum = 0;
+                timeRecord1.push_back(since(t0));
+                dd->garbageCollect();
+                const double ddSize = static_cast<double>(dd->size(rootEdge));
+                if (emaSwitchTest(ddSize)) {
+                    doSwitch(opNum);
+                    const auto tm = Clock::now();
+                    schedule = buildSchedule(opNum + 1);
+                    gateMergingTime = since(tm);
+                    if (verbose) {
+                        std::cout << "Gate merging time: " << gateMergingTime << '\n';
+                    }
+                    unitaryOps = opNum + 1;
+                    break;
+                }
+                EMA_v = pendingEma;
+                group = dd->makeIdent(qc->getNqubits());
+            }
+            ++opNum;
+            unitaryOps = opNum;
+        }
+        if (switched) {
+            execute(schedule);
+        } else if (verbose) {
+            std::cout << "Merged Gate Number: 0\n";
+        }
+    }
+
+    // enable_switch == false (src/SwitchSimulator.cpp:415-587): array from the first gate on
+    void runAllArray(bool ignoreNonUnitaries) {
+        getVectorFromDD();
+        switched = true;
+        switchedAtOp = 0;
+        if (fuse == 0) {
+            std::size_t opNum = 0;
+            const auto t0 = Clock::now();
+            for (auto& op : *qc) {
+                if (skipped(op, ignoreNonUnitaries)) {
+                    continue;
+                }
+                auto gate = DdOps::getDD(op.get(), dd);
+                if (!isIdentity(gate)) {
+                    launch(gate, 1);
+                } else {
+                    ++arrayPhaseOps;
+                }
+                dd->garbageCollect();
+                ++opNum;
+            }
+            unitaryOps = opNum;
+            backend->synchronize();
+            arrayPhaseTime = since(t0);
+            return;
+        }
+        const auto tm = Clock::now();
+        // the reference's no-switch greedy uses the IP cost only (:483-529); the result is a
+        // schedule of the same kind, so the shared builder is used here
+        Schedule schedule = buildSchedule(0);
+        gateMergingTime = since(tm);
+        if (verbose) {
+            std::cout << "Gate merging time: " << gateMergingTime << '\n';
+        }
+        execute(schedule);
+    }
+
+    // [a 0; 0 a] with a == 1 on every level and unit root weight
+    bool isIdentity(const MEdge& g) const {
+        if (WeightTraits::re(g.w) != 1.0 || WeightTraits::im(g.w) != 0.0) {
+            return false;
+        }
+        auto p = g.p;
+        while (p != nullptr) {
+            const auto& e = p->e;
+            if (!WeightTraits::isZero(e[1].w) || !WeightTraits::isZero(e[2].w) || e[0].p != e[3].p ||
+                WeightTraits::re(e[0].w) != 1.0 || WeightTraits::im(e[0].w) != 0.0 || WeightTraits::re(e[3].w) != 1.0 ||
+                WeightTraits::im(e[3].w) != 0.0) {
+                return false;
+            }
+            p = e[0].p;
+        }
+        return true;
+    }
+
+    void materialise() {
+        if (hostValid) {
+            return;
+        }
+        const std::size_t dim = std::size_t{1} << qc->getNqubits();
+        hostReal.assign(dim, 0.0);
+        hostImag.assign(dim, 0.0);
+        if (!onDevice) {
+            getVectorFromDD();
+        }
+        backend->getState(hostReal.data(), hostImag.data());
+        hostValid = true;
+    }
+
+    std::unique_ptr<Qc> qc;
+    ArrayBackend* backend;
+    double pendingEma = 0.0;
+    bool onDevice = false;
+    bool hostValid = false;
+    std::vector<fp> hostReal;
+    std::vector<fp> hostImag;
+};
+
+} // namespace fddb200

@@ -1,0 +1,177 @@
+/*
+ * flatdd_b200.h — C-ABI of the B200-native FlatDD array-phase hot path.
+ *
+ * The reference (IDEA-CUHK/FlatDD) has no FFI layer: its boundary for this path is a set of
+ * C++ member functions that take a decision-diagram edge plus raw `double*` arrays.  Every
+ * entry point below names the reference interface it replaces (file:line under the reference
+ * tree).  Signatures use only plain pointers and sizes, so cgo / JNI / ctypes / a C++ host can
+ * bind them alike.  All functions return 0 on success and a negative FDD_ERR_* code on
+ * failure; `fdd_last_error()` gives the message of the last failure on the calling thread.
+ *
+ * Index convention (reference: include/dd/SwitchPackage.hpp:3597):
+ * qubit q is bit q of the amplitude index, qubit 0 = least significant bit, and the top
+ * decision-diagram node carries level n-1.
+ */
+#ifndef FLATDD_B200_H
+#define FLATDD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDD_OK 0
+#define FDD_ERR_INVALID (-1)  /* malformed table / bad argument                      */
+#define FDD_ERR_CUDA (-2)     /* a CUDA runtime call failed (message has the detail) */
+#define FDD_ERR_TOO_DENSE (-3) /* gate has more non-zeros per row than one launch supports; split it */
+#define FDD_ERR_STATE (-4)    /* call not valid in the current state of the context  */
+#define FDD_ERR_COMM (-5)     /* multi-GPU exchange failed                            */
+
+/* Terminal / zero child index inside the flat tables. */
+#define FDD_TERMINAL (-1)
+
+/*
+ * Flat vector DD (the state DD, reference types vNode/vEdge: include/dd/Node.hpp:17-27,
+ * include/dd/Edge.hpp:12-14).  Node i has level `level[i]`, successor `child[2*i+b]` for
+ * bit value b of its qubit and edge weight (weight[2*(2*i+b)], weight[2*(2*i+b)+1]) = (re, im).
+ * A zero edge has child == FDD_TERMINAL and weight exactly (0,0) (the reference's
+ * `w.exactlyZero()` predicate).  Children are exactly one level below their parent
+ * (reference makeDDNode assert, include/dd/SwitchPackage.hpp:1251); level-0 nodes point to
+ * FDD_TERMINAL.  Nodes may come in any order.
+ */
+typedef struct fdd_vecdd {
+    int32_t n_qubits;
+    int32_t n_nodes;
+    int32_t root;          /* index of the root node (level n_qubits-1) */
+    int32_t reserved;
+    double root_weight[2]; /* (re, im) of the root edge */
+    const int32_t* level;  /* [n_nodes]   */
+    const int32_t* child;  /* [2*n_nodes] */
+    const double* weight;  /* [4*n_nodes] */
+} fdd_vecdd;
+
+/*
+ * Flat matrix DD (a gate, reference types mNode/mEdge: include/dd/Node.hpp:35-83).
+ * Successor index is 2*row_bit + col_bit exactly like `mNode::e[4]`; the DD is full depth
+ * (every level n-1..0 has a node on every non-zero path; identity levels are explicit),
+ * which is what makeGateDD / makeIdent / multiply produce
+ * (include/dd/SwitchPackage.hpp:694-775, 2922-2960) and what DDArrMultiplyRecurIP asserts (:2251).
+ */
+typedef struct fdd_matdd {
+    int32_t n_qubits;
+    int32_t n_nodes;
+    int32_t root;
+    int32_t reserved;
+    double root_weight[2];
+    const int32_t* level;  /* [n_nodes]   */
+    const int32_t* child;  /* [4*n_nodes] */
+    const double* weight;  /* [8*n_nodes] */
+} fdd_matdd;
+
+typedef struct fdd_ctx fdd_ctx;   /* one simulator state living on one GPU (or one shard of it) */
+typedef struct fdd_gate fdd_gate; /* a gate compiled for the device (tables resident in HBM)     */
+
+/* ---- library ------------------------------------------------------------------------- */
+const char* fdd_version(void);
+const char* fdd_last_error(void);
+/* Number of CUDA devices visible; fails (FDD_ERR_CUDA) when there is none: there is no CPU fallback. */
+int fdd_device_count(int* count);
+
+/* ---- context = the state buffers -------------------------------------------------------
+ * Replaces the SwitchSimulator constructor / destructor, which malloc and zero four
+ * double[2^n] arrays (include/SwitchSimulator.hpp:26-49), and the double-buffer protocol of
+ * singleShot (src/SwitchSimulator.cpp:143-151, 398-403).  The device state is two
+ * interleaved complex<double> buffers of 2^n_local amplitudes (ping-pong); gate kernels
+ * overwrite their destination, so there is no memset contract.
+ *
+ * world_size > 1 creates one shard of a state distributed over `world_size` contexts (one
+ * per process / GPU): rank r holds the amplitudes whose top log2(world_size) *physical* index
+ * bits equal r.  world_size must be a power of two. */
+int fdd_create(int n_qubits, int device, fdd_ctx** out);
+int fdd_create_sharded(int n_qubits, int device, int rank, int world_size, fdd_ctx** out);
+int fdd_destroy(fdd_ctx* ctx);
+int fdd_n_qubits(const fdd_ctx* ctx);
+int fdd_n_local_qubits(const fdd_ctx* ctx);
+int fdd_synchronize(fdd_ctx* ctx);
+/* Tunables for experiments ("dmavm_variant", "warps_per_cta", "ctas_per_sm", "prefetch", "exact_convert"). */
+int fdd_set_option(fdd_ctx* ctx, const char* key, long value);
+
+/* ---- multi-GPU wiring (one process per GPU) ---------------------------------------------
+ * fdd_comm_unique_id fills a 128-byte NCCL unique id on rank 0; the host broadcasts it
+ * (torch.distributed / MPI / a file) and every rank calls fdd_comm_init with it. */
+int fdd_comm_unique_id(void* id128);
+int fdd_comm_init(fdd_ctx* ctx, const void* id128);
+
+/* ---- DD -> array conversion -------------------------------------------------------------
+ * Replaces SwitchSimulator::getVectorFromDDSwitch1 (include/SwitchSimulator.hpp:169-352) and
+ * getVectorFromDD (:66-82) + getValueByPathPar (include/dd/SwitchPackage.hpp:3605-3634):
+ * amplitude(i) = w_root * prod_{v=n-1..0} w(node_v.e[bit_v(i)]), multiplied root first, leaf
+ * last, with un-fused IEEE multiplies/adds (bit-identical to the reference's serial walk).
+ * Every amplitude is written (zeros included).  The result becomes the current state. */
+int fdd_convert(fdd_ctx* ctx, const fdd_vecdd* dd);
+
+/* ---- DMAVM: gate (matrix DD) x state (array) --------------------------------------------
+ * Replaces SwitchPackage::DDArrMultiplyIP (include/dd/SwitchPackage.hpp:1897-1925,
+ * 2132-2261) and DDArrMultiplyOP (:1928-1956, 2265-2508): z[r] = sum_c M[r][c] * y[c] with
+ * M[r][c] = w_root * prod_v w(node_v.e[2*bit_v(r)+bit_v(c)]), summed over c ascending.  The
+ * result becomes the current state (the context flips its ping-pong buffers, which replaces
+ * the caller-side memset of the old buffer, src/SwitchSimulator.cpp:150-151). */
+int fdd_apply(fdd_ctx* ctx, const fdd_matdd* gate);
+/* Same in two steps, so a schedule can be compiled once and replayed. */
+int fdd_gate_compile(fdd_ctx* ctx, const fdd_matdd* gate, fdd_gate** out);
+int fdd_gate_apply(fdd_ctx* ctx, const fdd_gate* gate);
+int fdd_gate_free(fdd_gate* gate);
+/* Facts about a compiled gate: key in {"kind","max_paths","max_sub_k","upper_nodes","sub_tables","nnz_per_row_max","global_levels"}. */
+long fdd_gate_info(const fdd_gate* gate, const char* key);
+
+/* Literal drop-in for one DDArrMultiplyIP call on HOST arrays (SoA re/im, nDim = 2^n):
+ * uploads y, multiplies, downloads z (z is overwritten, not accumulated). */
+int fdd_ddarr_multiply(const fdd_matdd* gate, const double* y_real, const double* y_imag,
+                       double* z_real, double* z_imag, size_t n_dim, int device);
+
+/* ---- cost model (host only) ---------------------------------------------------------------
+ * fdd_mac_count = DMAVMACCountIP of the root (include/dd/SwitchPackage.hpp:3285-3311): the
+ * number of non-zero root-to-terminal paths = nnz of the matrix.
+ * fdd_cost_ip   = DMAVMACStatIP (:3012-3017) = nnz / 2^n_thread_exp.
+ * fdd_cost_op1  = DMAVMACStatOP1 (:3006-3010, 3202-3283).
+ * fdd_cost_gpu  = estimated device nanoseconds of one launch under the HBM / fp64 roofline
+ *                 (the re-tuned cost that drives GPU-aware fusion). */
+int fdd_mac_count(const fdd_matdd* gate, uint64_t* nnz);
+int fdd_cost_ip(const fdd_matdd* gate, unsigned n_thread_exp, uint64_t* cost);
+int fdd_cost_op1(const fdd_matdd* gate, unsigned n_thread_exp, uint64_t* cost);
+int fdd_cost_gpu(const fdd_matdd* gate, double hbm_gbs, double fp64_gflops, double* nanoseconds);
+
+/* ---- state access ---------------------------------------------------------------------------
+ * fdd_get_state replaces SwitchSimulator::getVector (include/SwitchSimulator.hpp:55-63): it
+ * synchronises and copies the current state into host SoA arrays of 2^n_local doubles each
+ * (the reference's state_real / state_imag layout).  Sharded contexts return their shard in
+ * logical order only after fdd_canonicalize (which undoes the global/local qubit remap). */
+int fdd_get_state(fdd_ctx* ctx, double* real, double* imag);
+int fdd_set_state(fdd_ctx* ctx, const double* real, const double* imag);
+/* |0...0> without a DD (reference: makeZeroState + conversion). */
+int fdd_set_zero_state(fdd_ctx* ctx);
+/* Read `count` amplitudes starting at local index `first` (interleaved re,im pairs). */
+int fdd_get_amplitudes(fdd_ctx* ctx, uint64_t first, uint64_t count, double* interleaved);
+/* sum |amp|^2 over the local shard, computed on the device. */
+int fdd_norm2(fdd_ctx* ctx, double* out);
+/* Device pointer of the current state (interleaved complex<double>), for zero-copy hosts. */
+int fdd_state_device_ptr(fdd_ctx* ctx, void** ptr);
+/* Sharded contexts: logical->physical qubit map (length n_qubits) and its undo. */
+int fdd_get_permutation(const fdd_ctx* ctx, int32_t* logical_to_physical);
+int fdd_canonicalize(fdd_ctx* ctx);
+
+/* ---- measurement hooks ----------------------------------------------------------------------
+ * Device time (CUDA events on the context's stream) of the last convert / gate launch, and
+ * the number of kernels the library has launched on this context since creation. */
+int fdd_last_kernel_ms(fdd_ctx* ctx, float* ms);
+int fdd_set_timing(fdd_ctx* ctx, int enabled);
+uint64_t fdd_launch_count(const fdd_ctx* ctx);
+/* The CUDA stream (cudaStream_t) kernels are launched on. */
+int fdd_stream(fdd_ctx* ctx, void** stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLATDD_B200_H */

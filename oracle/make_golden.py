@@ -1,0 +1,99 @@
+"""Regenerates the golden fixtures by running the compiled reference (oracle/_ref/ref_dump).
+
+    python oracle/make_golden.py small     # tests/golden/<case>/   (committed)
+    python oracle/make_golden.py medium    # oracle/_ref/golden/<case>/ (git-ignored, travels with gpurun)
+    python oracle/make_golden.py large     # samples only, minutes to tens of minutes of CPU
+    python oracle/make_golden.py traces    # boundary traces of the bench circuits (no reference run)
+
+Needs /root/reference (for `make -C oracle ref`) and the repo's own test circuits."""
+from __future__ import annotations
+
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+REF = Path("/root/reference")
+DUMP = ROOT / "oracle" / "_ref" / "ref_dump"
+
+# case name -> (circuit, threads, fuse, extra args)
+SMALL = {
+    "tiny_n3_f0": ("tests/circuits/tiny_n3.qasm", 1, 0, ["--kat-gates", "3"]),
+    "tiny_n3_f1": ("tests/circuits/tiny_n3.qasm", 1, 1, ["--kat-gates", "2"]),
+    "small_n5_f0": ("tests/circuits/small_n5.qasm", 2, 0, ["--kat-gates", "3"]),
+    "small_n5_f1": ("tests/circuits/small_n5.qasm", 2, 1, ["--kat-gates", "2"]),
+    "mix_n7_f0": ("tests/circuits/mix_n7.qasm", 4, 0, ["--kat-gates", "4"]),
+    "mix_n7_f1": ("tests/circuits/mix_n7.qasm", 4, 1, ["--kat-gates", "2"]),
+    "qft_n8_f0": ("tests/circuits/qft_n8.qasm", 4, 0, ["--kat-gates", "3"]),
+    "qft_n8_f1": ("tests/circuits/qft_n8.qasm", 4, 1, ["--kat-gates", "2"]),
+    "ghz_n6_f0": ("tests/circuits/ghz_n6.qasm", 4, 0, ["--kat-gates", "2"]),
+    "mix_n10_f0": ("tests/circuits/mix_n10.qasm", 4, 0, ["--kat-gates", "4"]),
+    "mix_n10_f1": ("tests/circuits/mix_n10.qasm", 4, 1, ["--kat-gates", "2"]),
+    "mix_n10_f1nc": ("tests/circuits/mix_n10.qasm", 4, 1, ["--kat-gates", "1", "--no_cache"]),
+    "mix_n10_f2": ("tests/circuits/mix_n10.qasm", 4, 2, ["--kat-gates", "1"]),
+    "brick_n11_f1": ("tests/circuits/brick_n11.qasm", 8, 1, ["--kat-gates", "1"]),
+    "mix_n12_f0": ("tests/circuits/mix_n12.qasm", 8, 0, ["--kat-gates", "1"]),
+    "mix_n12_f1": ("tests/circuits/mix_n12.qasm", 8, 1, ["--kat-gates", "1"]),
+}
+MEDIUM = {
+    "vqe_n16_f0": (REF / "circuits/vqe_n16.qasm", 8, 0, ["--kat-gates", "2", "--full-state"]),
+    "vqe_n16_f1": (REF / "circuits/vqe_n16.qasm", 8, 1, ["--kat-gates", "1", "--full-state"]),
+    "dnn_n16_f1": (REF / "circuits/dnn_n16.qasm", 8, 1, ["--kat-gates", "1", "--full-state"]),
+    "ghz_state_n23_f0": (REF / "circuits/ghz_state_n23.qasm", 8, 0, ["--no-kat"]),
+    "supremacy_n20_f1": (REF / "circuits/supremacy_n20.qasm", 8, 1, ["--no-kat", "--full-state"]),
+    "dnn_n20_f1": (REF / "circuits/dnn_n20.qasm", 8, 1, ["--no-kat"]),
+}
+LARGE = {
+    "knn_n25_f1": (REF / "circuits/knn_n25.qasm", 8, 1, ["--no-kat"]),
+    "swap_test_n25_f1": (REF / "circuits/swap_test_n25.qasm", 8, 1, ["--no-kat"]),
+    "supremacy_n24_f1": (REF / "circuits/supremacy_n24.qasm", 8, 1, ["--no-kat"]),
+    "dnn_n25_f1": (REF / "circuits/dnn_n25.qasm", 8, 1, ["--no-kat"]),
+    "supremacy_n26_f1": (REF / "circuits/supremacy_n26.qasm", 8, 1, ["--no-kat"]),
+}
+# traces only (host DD phase + fusion schedule, no reference array phase): name -> (circuit, fuse)
+TRACES = {
+    "supremacy_n26_gpu": (REF / "circuits/supremacy_n26.qasm", 3),
+    "supremacy_n26_ref": (REF / "circuits/supremacy_n26.qasm", 1),
+    "supremacy_n24_gpu": (REF / "circuits/supremacy_n24.qasm", 3),
+    "supremacy_n20_gpu": (REF / "circuits/supremacy_n20.qasm", 3),
+    "dnn_n25_gpu": (REF / "circuits/dnn_n25.qasm", 3),
+    "knn_n25_gpu": (REF / "circuits/knn_n25.qasm", 3),
+    "swap_test_n25_gpu": (REF / "circuits/swap_test_n25.qasm", 3),
+    "vqe_n16_gpu": (REF / "circuits/vqe_n16.qasm", 3),
+}
+
+
+def run_case(out_root: Path, name: str, circuit, threads: int, fuse: int, extra):
+    out = out_root / name
+    out.mkdir(parents=True, exist_ok=True)
+    cmd = [str(DUMP), "--file", str(ROOT / circuit if not Path(circuit).is_absolute() else circuit), "--out", str(out),
+           "-t", str(threads), "--fuse", str(fuse)] + list(extra)
+    print(" ".join(cmd), flush=True)
+    with open(out / "ref_dump.log", "w") as log:
+        subprocess.run(cmd, check=True, stdout=log, stderr=subprocess.STDOUT)
+
+
+def main(argv):
+    what = argv[1] if len(argv) > 1 else "small"
+    only = set(argv[2:])
+    if not DUMP.exists():
+        subprocess.run(["make", "-C", str(ROOT / "oracle"), "ref"], check=True)
+    if what == "small":
+        for name, (c, t, f, extra) in SMALL.items():
+            if not only or name in only:
+                run_case(ROOT / "tests" / "golden", name, c, t, f, ["--full-state"] + extra)
+    elif what in ("medium", "large"):
+        table = MEDIUM if what == "medium" else LARGE
+        for name, (c, t, f, extra) in table.items():
+            if not only or name in only:
+                run_case(ROOT / "oracle" / "_ref" / "golden", name, c, t, f, extra)
+    elif what == "traces":
+        for name, (c, f) in TRACES.items():
+            if not only or name in only:
+                run_case(ROOT / "oracle" / "_ref" / "traces", name, c, 8, 1, ["--trace-fuse", str(f), "--no-ref"])
+    else:
+        raise SystemExit(__doc__)
+
+
+if __name__ == "__main__":
+    main(sys.argv)
