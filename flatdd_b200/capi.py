@@ -26,7 +26,7 @@ EXPORTS = [
     "fdd_version", "fdd_last_error", "fdd_device_count", "fdd_create", "fdd_create_sharded", "fdd_destroy",
     "fdd_n_qubits", "fdd_n_local_qubits", "fdd_synchronize", "fdd_set_option", "fdd_comm_unique_id", "fdd_comm_init",
     "fdd_convert", "fdd_apply", "fdd_gate_compile", "fdd_gate_apply", "fdd_gate_free", "fdd_gate_info",
-    "fdd_ddarr_multiply", "fdd_mac_count", "fdd_cost_ip", "fdd_cost_op1", "fdd_cost_gpu", "fdd_get_state",
+    "fdd_ddarr_multiply", "fdd_mac_count", "fdd_cost_ip", "fdd_cost_op1", "fdd_cost_gpu", "fdd_matdd_info", "fdd_get_state",
     "fdd_set_state", "fdd_set_zero_state", "fdd_get_amplitudes", "fdd_norm2", "fdd_state_device_ptr",
     "fdd_get_permutation", "fdd_canonicalize", "fdd_last_kernel_ms", "fdd_set_timing", "fdd_launch_count", "fdd_stream",
 ]
@@ -68,6 +68,7 @@ class Library:
         L.fdd_cost_ip.argtypes = [ddp, ctypes.c_uint, ctypes.POINTER(ctypes.c_uint64)]
         L.fdd_cost_op1.argtypes = [ddp, ctypes.c_uint, ctypes.POINTER(ctypes.c_uint64)]
         L.fdd_cost_gpu.argtypes = [ddp, ctypes.c_double, ctypes.c_double, dp]
+        L.fdd_matdd_info.argtypes = [ddp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_long)]
         L.fdd_get_state.argtypes = [vp, dp, dp]
         L.fdd_set_state.argtypes = [vp, dp, dp]
         L.fdd_set_zero_state.argtypes = [vp]
@@ -117,6 +118,12 @@ class Library:
         out = ctypes.c_double(0)
         c = gate.as_c()
         self.check(self.lib.fdd_cost_gpu(ctypes.byref(c), hbm_gbs, fp64_gflops, ctypes.byref(out)))
+        return out.value
+
+    def matdd_info(self, gate: FlatDD, key: str) -> int:
+        out = ctypes.c_long(0)
+        c = gate.as_c()
+        self.check(self.lib.fdd_matdd_info(ctypes.byref(c), key.encode(), ctypes.byref(out)))
         return out.value
 
     def ddarr_multiply(self, gate: FlatDD, y_re: np.ndarray, y_im: np.ndarray, device: int = 0):

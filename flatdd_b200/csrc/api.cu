@@ -432,10 +432,7 @@ int fdd_gate_free(fdd_gate* gate) {
     return FDD_OK;
 }
 
-long fdd_gate_info(const fdd_gate* gate, const char* key) {
-    if (gate == nullptr || key == nullptr) return -1;
-    const std::string k = key;
-    const CompiledGate& h = gate->host;
+static long gateFact(const CompiledGate& h, const std::string& k) {
     if (k == "kind") return h.diagonal ? 1 : 0;
     if (k == "max_paths") return h.maxPaths;
     if (k == "max_sub_k") return h.kMax;
@@ -445,7 +442,20 @@ long fdd_gate_info(const fdd_gate* gate, const char* key) {
     if (k == "top_level") return h.topLevel;
     if (k == "upper_depth") return h.upperDepth;
     if (k == "stack_cap") return h.stackCap;
+    if (k == "nnz") return static_cast<long>(h.nnz);
     return -1;
+}
+
+long fdd_gate_info(const fdd_gate* gate, const char* key) {
+    if (gate == nullptr || key == nullptr) return -1;
+    return gateFact(gate->host, key);
+}
+
+int fdd_matdd_info(const fdd_matdd* gate, const char* key, long* value) {
+    return guarded([&] {
+        if (gate == nullptr || key == nullptr || value == nullptr) throw std::invalid_argument("null argument");
+        *value = gateFact(compileGate(*gate), key);
+    });
 }
 
 int fdd_apply(fdd_ctx* ctx, const fdd_matdd* gate) {

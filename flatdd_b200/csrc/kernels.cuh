@@ -285,7 +285,9 @@ template <int VARIANT> __global__ void __launch_bounds__(512) dmavm_walk_kernel(
             int sp = 0;
             int code = p.root;
             double2 w = p.rootW;
-            uint32_t col = 0;
+            // identity-compressed levels copy the row bit into the column: start from the row's own
+            // segment and overwrite the bit of every level that is actually visited
+            uint32_t col = rowSeg;
             for (;;) {
                 while (code >= 0) {
                     const UpperNode& nd = upper[code];
@@ -302,6 +304,7 @@ template <int VARIANT> __global__ void __launch_bounds__(512) dmavm_walk_kernel(
                             ++sp;
                         }
                         w = cmul(w, nw[0]);
+                        col &= ~(1u << sh);
                         code = ch.x;
                     } else if (ch.y != FDD_TERMINAL) {
                         w = cmul(w, nw[1]);

@@ -142,6 +142,8 @@ int fdd_mac_count(const fdd_matdd* gate, uint64_t* nnz);
 int fdd_cost_ip(const fdd_matdd* gate, unsigned n_thread_exp, uint64_t* cost);
 int fdd_cost_op1(const fdd_matdd* gate, unsigned n_thread_exp, uint64_t* cost);
 int fdd_cost_gpu(const fdd_matdd* gate, double hbm_gbs, double fp64_gflops, double* nanoseconds);
+/* Host-only structural facts of a gate, same keys as fdd_gate_info (no device needed). */
+int fdd_matdd_info(const fdd_matdd* gate, const char* key, long* value);
 
 /* ---- state access ---------------------------------------------------------------------------
  * fdd_get_state replaces SwitchSimulator::getVector (include/SwitchSimulator.hpp:55-63): it
