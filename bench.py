@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py — array-phase throughput of FlatDD's hot path on B200.
+
+Workload (BASELINE.json configs[1]): circuits/supremacy_n26.qasm with DMAVM-aware gate fusion on
+one B200.  One STEP = one pass of the hot path over that circuit: the DD->array conversion of the
+state DD at the reference's switch point (after op 911) plus one DMAVM launch per fused gate of
+the schedule (5078 circuit operations in the array phase).  The inputs are the flat DD tables the
+host driver (flatdd_b200/host/gpu_switch_simulator.hpp) emits for that circuit, recorded at build
+time into a boundary trace (oracle/_ref/traces/, a committed copy under tests/golden/traces/);
+nothing here reads /root/reference.
+
+Metric: array-phase circuit operations per second ("gates/s"); seconds per circuit is echoed.
+  value  kernels only, gate tables resident in HBM (compiled once), CUDA events on the library stream
+  e2e    the same step through the host-buffer C-ABI: fdd_convert + fdd_apply per gate (gate
+         compilation and table upload inside) + fdd_get_state into pinned host memory
+  roofline  dmavm_walk_kernel: 32 * 2^n algorithmic bytes per launch / mean launch time vs the
+         measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the unmodified reference CLI (oracle/_ref/FlatDD) on this box's host cores on a
+         bounded sample of the same circuit (first 40 array-phase operations)
+
+`--impl reference` times that reference CLI alone and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import gzip
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+WORKLOAD = "supremacy_n26"
+METRIC = "array_phase_gates_per_sec"
+UNIT = "gates/s"
+SAMPLE_OPS = 40  # array-phase operations in the CPU sample circuit
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def find_trace(name: str) -> Path:
+    travel = ROOT / "oracle" / "_ref" / "traces" / name / "trace.bin"
+    if travel.exists():
+        return travel
+    packed = ROOT / "tests" / "golden" / "traces" / f"{name}.trace.gz"
+    if packed.exists():
+        out = Path(tempfile.gettempdir()) / f"flatdd_b200_{name}.trace.bin"
+        if not out.exists() or out.stat().st_mtime < packed.stat().st_mtime:
+            with gzip.open(packed, "rb") as src, open(out, "wb") as dst:
+                shutil.copyfileobj(src, dst)
+        return out
+    raise FileNotFoundError(f"no boundary trace for {name}: run `python oracle/make_golden.py traces` where the reference tree exists")
+
+
+def table_bytes(dd) -> int:
+    return dd.level.nbytes + dd.child.nbytes + dd.weight.nbytes + 32
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi while the timed region runs (B200_PROFILING.md clocks line)."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.device_index = device_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._thread = None
+        self._proc = None
+
+    def start(self):
+        if shutil.which("nvidia-smi") is None:
+            return
+        self._proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+
+        def pump():
+            for line in self._proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self._stop.is_set():
+                    break
+
+        self._thread = threading.Thread(target=pump, daemon=True)
+        self._thread.start()
+
+    def stop(self) -> dict:
+        self._stop.set()
+        if self._proc is not None:
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=2)
+            except Exception:
+                self._proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for name, cell in zip(names, r[5:9]):
+                if cell.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference CPU arm
+# ------------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    cores = os.cpu_count() or 1
+    t = 1
+    while t * 2 <= min(cores, 16):
+        t *= 2
+    return t
+
+
+def sample_circuit() -> Path:
+    p = ROOT / "oracle" / "_ref" / "circuits" / f"{WORKLOAD}_sample.qasm"
+    if not p.exists():
+        raise FileNotFoundError(f"{p} missing: run `python oracle/make_golden.py samples` where the reference tree exists")
+    return p
+
+
+def run_reference_once(threads: int) -> dict:
+    """One run of the unmodified reference CLI on the sample circuit; returns its own timings."""
+    exe = ROOT / "oracle" / "_ref" / "FlatDD"
+    if not exe.exists():
+        raise FileNotFoundError(f"{exe} missing: run `make -C oracle ref` where the reference tree exists")
+    circuit = sample_circuit()
+    meta = json.loads((circuit.parent / f"{WORKLOAD}_sample.json").read_text())
+    with tempfile.TemporaryDirectory() as tmp:
+        cwd = Path(tmp) / "build" / "apps"  # the CLI writes to ../../log/results relative to its cwd
+        cwd.mkdir(parents=True)
+        (Path(tmp) / "log" / "results" / "time").mkdir(parents=True)
+        (Path(tmp) / "log" / "results" / "state").mkdir(parents=True)
+        t0 = time.perf_counter()
+        out = subprocess.run([str(exe), "--file", str(circuit), "-t", str(threads), "--fuse", "1"], cwd=cwd, capture_output=True,
+                             text=True, check=True).stdout
+        wall = time.perf_counter() - t0
+        time_file = next((Path(tmp) / "log" / "results" / "time").glob("*_FlatDD.txt"))
+        lines = time_file.read_text().splitlines()
+    k = next(i for i, line in enumerate(lines) if line.startswith("Switch Overhead:"))
+    convert_s = float(lines[k].split(":")[1])
+    array_times = [float(x) for x in lines[k + 1:] if x.strip()]
+    switched_at = None
+    for line in out.splitlines():
+        if line.startswith("Switching at instr."):
+            switched_at = int(line.split()[-1])
+    array_ops = meta["unitary_ops"] - (switched_at + 1)
+    return {"array_s": sum(array_times), "convert_s": convert_s, "launches": len(array_times), "array_ops": array_ops,
+            "wall_s": wall, "switched_at": switched_at}
+
+
+def reference_arm(args) -> int:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = host_threads()
+    for _ in range(args.warmup):
+        run_reference_once(threads)
+    runs = [run_reference_once(threads) for _ in range(args.steps)]
+    ops = sum(r["array_ops"] for r in runs)
+    secs = sum(r["array_s"] + r["convert_s"] for r in runs)
+    value = ops / secs
+    sample = (f"first {runs[0]['array_ops']} array-phase ops of {WORKLOAD} after the switch at op {runs[0]['switched_at']} "
+              f"({runs[0]['launches']} fused DMAVM calls, conversion included), reference CLI --fuse 1 -t {threads}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(runs)), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD} array phase (bounded sample)", "n_qubits": 26, "fusion": "reference greedy (--fuse 1)",
+                   "host_cores": os.cpu_count(), "threads": threads},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "seconds_per_circuit_extrapolated": 5078 / value,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def gpu_arm(args) -> int:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from flatdd_b200 import Context, load_library, read_trace
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: flatdd_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    lib = load_library()
+    n, records = read_trace(find_trace(f"{WORKLOAD}_gpu"))
+    assert records[0].kind == 1
+    vec = records[0].dd
+    gates = [r.dd for r in records[1:]]
+    array_ops = sum(r.n_original_gates for r in records[1:])
+    dim = 1 << n
+
+    # N > 1: every rank simulates an independent replica of the circuit (weak scaling over
+    # independent circuits) until the sharded exchange path lands; see DESIGN.md section (e).
+    ctx = Context(n, device=local_rank, library=lib)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+    compiled = [ctx.compile(g) for g in gates]
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_resident():
+        ctx.convert(vec)
+        for g in compiled:
+            ctx.apply_compiled(g)
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    barrier()
+
+    # ---- timed region: K steps, device time on the library's stream ---------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps)]
+    launches0 = ctx.launch_count()
+    barrier()
+    for s in range(args.steps):
+        ev[3 * s].record(stream)
+        ctx.convert(vec)
+        ev[3 * s + 1].record(stream)
+        for g in compiled:
+            ctx.apply_compiled(g)
+        ev[3 * s + 2].record(stream)
+    barrier()
+    launches = ctx.launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[3 * args.steps - 1])
+    convert_ms = [ev[3 * s].elapsed_time(ev[3 * s + 1]) for s in range(args.steps)]
+    gates_ms = [ev[3 * s + 1].elapsed_time(ev[3 * s + 2]) for s in range(args.steps)]
+    norm2 = ctx.norm2()
+
+    # ---- e2e: host buffers through the C-ABI, H2D of every table and D2H of the state ------------
+    host_re = torch.empty(dim, dtype=torch.float64).pin_memory()
+    host_im = torch.empty(dim, dtype=torch.float64).pin_memory()
+    h2d = table_bytes(vec) + sum(table_bytes(g) for g in gates)
+    d2h = 16 * dim
+
+    def step_e2e():
+        ctx.convert(vec)
+        for g in gates:
+            ctx.apply(g)
+        ctx.get_state_raw(host_re.data_ptr(), host_im.data_ptr())
+
+    step_e2e()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    clocks = sampler.stop()
+    host_norm2 = float(torch.dot(host_re, host_re) + torch.dot(host_im, host_im))
+
+    # ---- max over ranks ------------------------------------------------------------------------------
+    t_step_ms = total_ms / args.steps
+    if world > 1:
+        t = torch.tensor([t_step_ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_step_ms, e2e_s = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = {}
+        peaks_file = ROOT / "MEASURED_PEAKS.json"
+        if peaks_file.exists():
+            peaks = json.loads(peaks_file.read_text())
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        launch_ms = statistics.mean(gates_ms) / len(compiled)
+        achieved = 32.0 * dim / (launch_ms * 1e-3) / 1e9
+        traffic = None
+        tf = ROOT / "profiles" / "dmavm_traffic.json"
+        if tf.exists():
+            traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": world * array_ops / (t_step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": t_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{WORKLOAD} array phase: DD->array conversion + {len(compiled)} fused DMAVM launches "
+                                   f"({array_ops} circuit ops after the switch at op 911)",
+                       "n_qubits": n, "state_bytes": 16 * dim, "fusion": "GPU-cost greedy (fuse 3)",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas",
+                       "l2": "state (1 GiB) and its ping-pong partner exceed the 126 MB L2; no flush needed"},
+            "seconds_per_circuit": t_step_ms * 1e-3,
+            "convert_ms": statistics.mean(convert_ms), "dmavm_ms_per_launch": launch_ms,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "dmavm_walk_kernel", "peak_source": peak_src, "bytes_per_launch": 32 * dim,
+                         "convert_gbs": 16.0 * dim / (statistics.mean(convert_ms) * 1e-3) / 1e9},
+            "e2e": {"value": world * array_ops / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "seconds_per_circuit": e2e_s, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "check": {"norm2_device": norm2, "norm2_host_copy": host_norm2},
+        }
+        if world == 1 and not args.no_cpu:
+            try:
+                r = run_reference_once(host_threads())
+                secs = r["array_s"] + r["convert_s"]
+                line["cpu_baseline"] = {
+                    "value": r["array_ops"] / secs, "unit": UNIT, "cores": host_threads(), "kind": "reference",
+                    "sample": f"first {r['array_ops']} array-phase ops of {WORKLOAD} after the switch at op {r['switched_at']} "
+                              f"({r['launches']} fused DMAVM calls + conversion, {secs:.1f} s), unmodified reference CLI --fuse 1 "
+                              f"-t {host_threads()} on {os.cpu_count()} host cores"}
+            except Exception as exc:  # the baseline is reported, never allowed to void the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_threads(), "kind": "reference", "sample": f"failed: {exc}"}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="flatdd_b200", choices=["flatdd_b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

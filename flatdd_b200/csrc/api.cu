@@ -89,8 +89,8 @@ struct fdd_ctx {
     uint64_t launches = 0;
     int smCount = 148;
     // tunables
-    int variant = 1;
-    int warpsPerCta = 8;
+    int variant = 2;      // 2: tile kernel when the gate allows it, else 1; 1: cp.async ring walk; 0: register walk
+    int warpsPerCta = 0;  // 0 = chosen per launch
     int ctasPerSm = 0; // 0 = as many as shared memory allows (capped)
     int prefetch = 8;
     // scratch
@@ -191,13 +191,65 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
     int D = c->prefetch;
     if (D != 1 && D != 2 && D != 4 && D != 8 && D != 16) D = 8;
     p.prefetch = D;
-    const int variant = c->variant == 0 ? 0 : 1;
-
     const size_t tableBytes = walkTableSmem(p.nUpper, p.nSub, p.kMax);
     p.tablesInSmem = tableBytes <= kTableSmemLimit ? 1 : 0;
     const size_t fixed = p.tablesInSmem ? tableBytes : 0;
+
+    if (c->variant >= 2 && h.tileable && h.upper.size() < (1u << 22) && h.nSub < (1 << 22)) {
+        // ---- tile kernel ----------------------------------------------------------------------------
+        bool allIdentity = true;
+        for (uint8_t f : h.subFlags) allIdentity = allIdentity && (f & SUB_IDENTITY);
+        const int mode = allIdentity ? 0 : (h.nSub == 1 ? 1 : 2);
+        p.tileBits = h.tileBits;
+        p.subTileBits = h.subTileBits;
+        p.tileMask = h.tileMask;
+        p.fillMask = h.fillMask;
+        p.nTiles = p.nSeg >> h.tileBits;
+        const size_t perWarpT = tileWarpSmem(p.maxPaths, p.stackCap, h.subTileBits);
+        int bestW = 0, bestC = 0;
+        for (int ctas = 1; ctas <= 8; ++ctas) {
+            if (c->ctasPerSm > 0 && ctas > c->ctasPerSm) break;
+            const size_t avail = kSmemBudget / ctas;
+            if (avail < fixed + 1024 + perWarpT) break;
+            int w = static_cast<int>(std::min<size_t>(8, (avail - fixed - 1024) / perWarpT));
+            if (c->warpsPerCta > 0) w = std::min(w, c->warpsPerCta);
+            if (w * ctas > 32) continue; // resident-warp cap (registers: <= 128 per thread)
+            if (w * ctas > bestW * bestC) {
+                bestW = w;
+                bestC = ctas;
+            }
+        }
+        if (bestW > 0) {
+            const size_t smemT = fixed + static_cast<size_t>(bestW) * perWarpT;
+            const uint32_t ctasWantedT = (p.nTiles + bestW - 1) / bestW;
+            using Kernel = void (*)(const WalkParams);
+            static const Kernel table[6][3] = {
+                {dmavm_tile_kernel<0, 0>, dmavm_tile_kernel<0, 1>, dmavm_tile_kernel<0, 2>},
+                {dmavm_tile_kernel<1, 0>, dmavm_tile_kernel<1, 1>, dmavm_tile_kernel<1, 2>},
+                {dmavm_tile_kernel<2, 0>, dmavm_tile_kernel<2, 1>, dmavm_tile_kernel<2, 2>},
+                {dmavm_tile_kernel<3, 0>, dmavm_tile_kernel<3, 1>, dmavm_tile_kernel<3, 2>},
+                {dmavm_tile_kernel<4, 0>, dmavm_tile_kernel<4, 1>, dmavm_tile_kernel<4, 2>},
+                {dmavm_tile_kernel<5, 0>, dmavm_tile_kernel<5, 1>, dmavm_tile_kernel<5, 2>},
+            };
+            const Kernel kernel = table[h.subTileBits][mode];
+            CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
+            int resident = bestC;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, bestW * 32, smemT));
+            resident = std::max(1, std::min(resident, bestC));
+            const int gridT = static_cast<int>(std::max<uint32_t>(1, std::min<uint32_t>(ctasWantedT, static_cast<uint32_t>(c->smCount * resident))));
+            Timed t(c);
+            kernel<<<gridT, bestW * 32, smemT, c->stream>>>(p);
+            CUDA_TRY(cudaGetLastError());
+            c->launches++;
+            c->cur ^= 1;
+            return;
+        }
+        // the per-warp state does not fit: fall through to the walk kernel
+        p.nTiles = (p.nSeg + 31) / 32;
+    }
+    const int variant = c->variant == 0 ? 0 : 1;
     const size_t perWarp = walkWarpSmem(p.maxPaths, p.stackCap, variant == 1 ? D : 0);
-    int warps = std::max(1, std::min(c->warpsPerCta, 16));
+    int warps = std::max(1, std::min(c->warpsPerCta > 0 ? c->warpsPerCta : 8, 16));
     while (warps > 1 && fixed + warps * perWarp > kSmemBudget) warps >>= 1;
     if (fixed + warps * perWarp > kSmemBudget) {
         throw std::length_error("gate too dense for one launch: " + std::to_string(h.maxPaths) +
@@ -407,7 +459,7 @@ int fdd_gate_compile(fdd_ctx* ctx, const fdd_matdd* gate, fdd_gate** out) {
         useDevice(ctx);
         auto g = new fdd_gate();
         try {
-            g->host = compileGate(*gate);
+            g->host = compileGate(*gate, ctx->nLocal);
             g->device = ctx->device;
             uploadGate(g, ctx->stream);
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -443,6 +495,9 @@ static long gateFact(const CompiledGate& h, const std::string& k) {
     if (k == "upper_depth") return h.upperDepth;
     if (k == "stack_cap") return h.stackCap;
     if (k == "nnz") return static_cast<long>(h.nnz);
+    if (k == "tileable") return h.tileable ? 1 : 0;
+    if (k == "sub_tile_bits") return h.subTileBits;
+    if (k == "non_diag_upper") return h.nonDiagUpper;
     return -1;
 }
 
@@ -464,7 +519,7 @@ int fdd_apply(fdd_ctx* ctx, const fdd_matdd* gate) {
         useDevice(ctx);
         auto g = new fdd_gate();
         try {
-            g->host = compileGate(*gate);
+            g->host = compileGate(*gate, ctx->nLocal);
             g->device = ctx->device;
             uploadGate(g, ctx->stream);
             launchWalk(ctx, g);

@@ -159,8 +159,9 @@ uint64_t costOP1(const fdd_matdd& g, unsigned nThreadExp) {
     return cnt / nThread + nDim * buffers.size() / (4 * nThread);
 }
 
-CompiledGate compileGate(const fdd_matdd& g) {
+CompiledGate compileGate(const fdd_matdd& g, int nLocal) {
     validate(g);
+    if (nLocal < 0 || nLocal > g.n_qubits) nLocal = g.n_qubits;
     CompiledGate out;
     out.n = g.n_qubits;
     out.segBits = std::min(5, g.n_qubits);
@@ -359,6 +360,36 @@ CompiledGate compileGate(const fdd_matdd& g) {
     }
     out.nnz = macCount(g);
     out.nnzRowMax = out.maxPaths * out.kMax;
+
+    // ---- tile bits -----------------------------------------------------------------------------------
+    {
+        uint64_t nonDiag = 0; // bit (level - S) set when some reachable node of that level is off-diagonal
+        for (int32_t u = 0; u < g.n_nodes; ++u) {
+            if (!reach[static_cast<std::size_t>(u)] || g.level[u] < S) continue;
+            if (!isZero(W(u, 1)) || !isZero(W(u, 2))) nonDiag |= uint64_t{1} << (g.level[u] - S);
+        }
+        out.nonDiagUpper = __builtin_popcountll(nonDiag);
+        const int localSegBits = std::max(0, nLocal - S);
+        out.tileBits = std::min(5, localSegBits);
+        const bool allLocal = (nonDiag >> localSegBits) == 0;
+        out.tileable = allLocal && out.nonDiagUpper <= out.tileBits;
+        if (out.tileable) {
+            const uint32_t mask = static_cast<uint32_t>(nonDiag);
+            uint32_t fill = 0;
+            for (int b = 0; b < localSegBits && __builtin_popcount(mask | fill) < out.tileBits; ++b) {
+                if (!((mask >> b) & 1u)) fill |= 1u << b;
+            }
+            out.tileMask = mask;
+            out.fillMask = fill;
+            out.subTileBits = out.nonDiagUpper;
+            for (UpperNode& nd : out.upper) {
+                const int sh = nd.level - S;
+                nd.slotBit = (sh < 32 && ((mask >> sh) & 1u)) ? __builtin_popcount(mask & ((1u << sh) - 1u)) : -1;
+            }
+        } else {
+            for (UpperNode& nd : out.upper) nd.slotBit = -1;
+        }
+    }
     return out;
 }
 

@@ -27,7 +27,8 @@ namespace fddb200 {
 struct alignas(16) UpperNode {
     int32_t child[4]; // >= 0: upper node index; FDD_TERMINAL (-1): zero edge; <= -2: sub table (-2 - id)
     int32_t level;
-    int32_t pad[3];
+    int32_t slotBit;  // index of this level inside the tile bit set, -1 if the level is not a tile bit
+    int32_t pad[2];
     double w[8];      // (re, im) per successor
 };
 static_assert(sizeof(UpperNode) == 96, "UpperNode layout is shared with the device code");
@@ -60,12 +61,22 @@ struct CompiledGate {
     int nnzRowMax = 0;  // upper bound on non-zeros in one row (maxPaths * kMax)
     int topLevel = -1;  // highest level with a non-identity node (-1: scalar multiple of identity)
     bool diagonal = false; // every level diagonal
+    // tile-staged launch: the 2^tileBits segments of a tile differ in the index bits `tileMask`
+    // (positions relative to the segment index).  Valid when every upper level that is not
+    // diagonal fits into the tile, so that all sources of a tile lie in the tile itself.
+    bool tileable = false;
+    int tileBits = 0;      // log2(segments per warp tile)
+    int subTileBits = 0;   // popcount(tileMask)
+    uint32_t tileMask = 0; // index bits of the non-diagonal upper levels (a sub-tile is closed under the gate)
+    uint32_t fillMask = 0; // lowest free index bits that complete the warp tile
+    int nonDiagUpper = 0; // upper levels with an off-diagonal successor
 };
 
 // Throws std::runtime_error with a message on malformed input.
 void validate(const fdd_matdd& g);
 void validate(const fdd_vecdd& v);
-CompiledGate compileGate(const fdd_matdd& g);
+// nLocal: qubits held by one shard (== g.n_qubits on one GPU); tile bits are local bits.
+CompiledGate compileGate(const fdd_matdd& g, int nLocal = -1);
 
 // Reference cost model, same results as oracle/flat_oracle.c but
 // part of the product because the fusion pass consumes it.

@@ -191,6 +191,10 @@ struct WalkParams {
     uint32_t nTiles;
     int tablesInSmem;
     int prefetch;                     // ring depth D (variant 1)
+    int tileBits;                     // tile kernel: log2(segments per warp tile) (<= 5)
+    int subTileBits;                  // tile kernel: TB = number of bits in tileMask
+    uint32_t tileMask;                // tile kernel: segment-index bits of the non-diagonal upper levels
+    uint32_t fillMask;                // tile kernel: further index bits that complete the warp tile
 };
 
 // Bytes of shared memory one warp needs.
@@ -427,6 +431,275 @@ template <int VARIANT> __global__ void __launch_bounds__(512) dmavm_walk_kernel(
         }
         __syncwarp();
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// DMAVM tile kernel (the fast path)
+// ------------------------------------------------------------------------------------------------
+// Precondition (checked on the host, gate_compile.cpp "tile bits"): every upper level with an
+// off-diagonal successor is one of the TB segment-index bits in `tileMask`.  Then the T = 2^TB
+// segments that differ only in those bits form a SUB-TILE that is closed under the gate: every
+// source segment of an output segment lies in the same sub-tile.  Every amplitude is therefore
+// read from HBM once and written once — 32 B per amplitude, the algorithmic minimum — whatever
+// the number of non-zeros per row.
+//
+// A warp owns WARP TILES of 32 segments = Q sub-tiles (the sub-tile bits plus `fillMask` bits,
+// the lowest free index bits, so consecutive sub-tiles are neighbours in memory):
+//   phase A  lane = segment of the warp tile: depth-first walk of the upper levels, leaving per
+//            segment a list of (weight, source slot inside its sub-tile[, sub table]) in shared
+//            memory, padded with zero weights to `maxPaths` entries so phase B is branch-free;
+//   phase B  lane = amplitude: the sub-tiles stream through a per-warp ring of R stage slots
+//            filled by cp.async (16-byte vectors, one coalesced 512-byte request per segment).
+//            The ring is indexed by a running sub-tile counter, so copies for the next warp
+//            tile are already in flight while phase A of that tile runs.  The T output
+//            segments of a sub-tile are accumulated together (T independent FMA chains).
+// MODE 0: the low S levels are untouched (identity sub table)      z_j = sum_i w_ji y_slot(j,i)
+// MODE 1: one sub table L for the whole gate                        z_j = L (sum_i w_ji y_slot(j,i))
+//         (L applied across lanes with warp shuffles: the operator factorises as U (x) L)
+// MODE 2: sub table depends on the path                             general ELL gather
+template <int TB> struct TileShape {
+    static constexpr int T = 1 << TB;
+    static constexpr int R = (16 / T) < 2 ? 2 : (16 / T);
+    static constexpr int JC = T < 8 ? T : 8;
+};
+__host__ __device__ inline size_t tileWarpSmem(int maxPaths, int stackCap, int tileBits) {
+    const int T = 1 << tileBits;
+    const int R = (16 / T) < 2 ? 2 : (16 / T);
+    return static_cast<size_t>(maxPaths + stackCap) * 32 * 20 + static_cast<size_t>(R) * T * 512;
+}
+
+__device__ __forceinline__ uint32_t depositBits(uint32_t x, uint32_t mask) { // pdep
+    uint32_t out = 0;
+    for (uint32_t m = mask; m != 0; m &= m - 1) {
+        const uint32_t lowest = m & (0u - m);
+        if (x & 1u) out |= lowest;
+        x >>= 1;
+    }
+    return out;
+}
+// spread x over the zero bits of mask (mask has few bits set)
+__device__ __forceinline__ uint32_t depositAround(uint32_t x, uint32_t mask) {
+    for (uint32_t m = mask; m != 0; m &= m - 1) {
+        const uint32_t lowest = m & (0u - m);
+        x = ((x & ~(lowest - 1u)) << 1) | (x & (lowest - 1u));
+    }
+    return x;
+}
+
+template <int TB, int MODE> __global__ void __launch_bounds__(256, 2) dmavm_tile_kernel(const WalkParams p) {
+    constexpr int T = TileShape<TB>::T;
+    constexpr int R = TileShape<TB>::R;
+    constexpr int JC = TileShape<TB>::JC;
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    unsigned char* cursor = smemRaw;
+    const UpperNode* upper = p.upper;
+    const double2* subW = p.subW;
+    const uint8_t* subCol = p.subCol;
+    const int32_t* subK = p.subK;
+    if (p.tablesInSmem) {
+        UpperNode* su = reinterpret_cast<UpperNode*>(cursor);
+        cursor += static_cast<size_t>(p.nUpper) * sizeof(UpperNode);
+        double2* sw = reinterpret_cast<double2*>(cursor);
+        const int nEnt = p.nSub * p.kMax * 32;
+        cursor += static_cast<size_t>(nEnt) * 16;
+        int32_t* sk = reinterpret_cast<int32_t*>(cursor);
+        cursor += static_cast<size_t>(p.nSub) * 4;
+        uint8_t* sc = cursor;
+        {
+            const int4* src = reinterpret_cast<const int4*>(p.upper);
+            int4* dst = reinterpret_cast<int4*>(su);
+            for (int i = threadIdx.x; i < p.nUpper * 6; i += blockDim.x) dst[i] = src[i];
+        }
+        if (MODE != 0) {
+            for (int i = threadIdx.x; i < nEnt; i += blockDim.x) {
+                sw[i] = p.subW[i];
+                sc[i] = p.subCol[i];
+            }
+            for (int i = threadIdx.x; i < p.nSub; i += blockDim.x) sk[i] = p.subK[i];
+        }
+        __syncthreads();
+        upper = su;
+        subW = sw;
+        subCol = sc;
+        subK = sk;
+        cursor = smemRaw + walkTableSmem(p.nUpper, p.nSub, p.kMax);
+    }
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warpsPerCta = blockDim.x >> 5;
+    unsigned char* mine = cursor + static_cast<size_t>(warp) * tileWarpSmem(p.maxPaths, p.stackCap, TB);
+    const int nSlotsE = p.maxPaths + p.stackCap;
+    double2* eW = reinterpret_cast<double2*>(mine);                                               // [nSlotsE][32]
+    uint32_t* ePack = reinterpret_cast<uint32_t*>(mine + static_cast<size_t>(nSlotsE) * 32 * 16); // [nSlotsE][32]
+    double2* ring = reinterpret_cast<double2*>(mine + static_cast<size_t>(nSlotsE) * 32 * 20);    // [R][T][32]
+    const int stackBase = p.maxPaths;
+    const int P = p.maxPaths;
+
+    const uint32_t warpGlobal = blockIdx.x * warpsPerCta + warp;
+    const uint32_t warpStride = gridDim.x * warpsPerCta;
+    const int S = p.segBits;
+    const int segLen = 1 << S;
+    const int upperLocalBits = p.nLocal - S;
+    const int wtBits = p.tileBits;           // segments per warp tile = 2^wtBits (<= 32)
+    const int qBits = wtBits - TB;
+    const int Q = 1 << qBits;                // sub-tiles per warp tile
+    const int wtSegs = 1 << wtBits;
+    const uint32_t wtMask = p.tileMask | p.fillMask;
+    // lane l <-> segment (sub-tile q = l >> TB, slot t = l & (T-1)) of the warp tile
+    const uint32_t myDep = depositBits(static_cast<uint32_t>(lane) & (T - 1), p.tileMask) |
+                           depositBits(static_cast<uint32_t>(lane) >> TB, p.fillMask);
+    const uint32_t rankBits = p.rank << upperLocalBits;
+    if (warpGlobal >= p.nTiles) return;
+
+    // ---- copy pipeline state: running sub-tile counter over all warp tiles of this warp ---------
+    uint32_t issueTile = warpGlobal;
+    uint32_t issueBase = depositAround(issueTile, wtMask);
+    int issueQ = 0;
+    int issueSlot = 0;
+    auto issueNext = [&]() {
+        if (issueTile < p.nTiles) {
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const uint32_t dep = __shfl_sync(0xffffffffu, myDep, (issueQ << TB) | t);
+                if (lane < segLen) {
+                    cp_async16(ring + (issueSlot * T + t) * 32 + lane, p.y + ((static_cast<uint64_t>(issueBase | dep)) << S) + lane);
+                }
+            }
+            issueSlot = (issueSlot + 1 == R) ? 0 : issueSlot + 1;
+            if (++issueQ == Q) {
+                issueQ = 0;
+                issueTile += warpStride;
+                issueBase = depositAround(issueTile, wtMask);
+            }
+        }
+        cp_async_commit(); // one group per call (possibly empty) keeps the wait arithmetic uniform
+    };
+#pragma unroll
+    for (int r = 0; r < R; ++r) issueNext();
+    int useSlot = 0;
+
+    for (uint32_t tile = warpGlobal; tile < p.nTiles; tile += warpStride) {
+        const uint32_t base = depositAround(tile, wtMask);
+        // =================== phase A: upper walk, lane = segment of the warp tile =================
+        if (lane < wtSegs) {
+            int cnt = 0;
+            if (p.root != FDD_TERMINAL) {
+                const uint32_t rowSeg = rankBits | base | myDep;
+                const int tl = lane & (T - 1);
+                int sp = 0;
+                int code = p.root;
+                double2 w = p.rootW;
+                uint32_t slot = static_cast<uint32_t>(tl);
+                for (;;) {
+                    while (code >= 0) {
+                        const UpperNode& nd = upper[code];
+                        const int sb = nd.slotBit;
+                        const int rb = sb >= 0 ? ((tl >> sb) & 1) : static_cast<int>((rowSeg >> (nd.level - S)) & 1u);
+                        const uint32_t bit = sb >= 0 ? (1u << sb) : 0u;
+                        const int2 ch = *reinterpret_cast<const int2*>(&nd.child[2 * rb]);
+                        const double2* nw = reinterpret_cast<const double2*>(nd.w) + 2 * rb;
+                        if (ch.x != FDD_TERMINAL) {
+                            if (ch.y != FDD_TERMINAL) {
+                                const int at = (stackBase + sp) * 32 + lane;
+                                eW[at] = cmul(w, nw[1]);
+                                ePack[at] = (static_cast<uint32_t>(ch.y) & 0xffffffu) | ((slot | bit) << 24);
+                                ++sp;
+                            }
+                            w = cmul(w, nw[0]);
+                            slot &= ~bit;
+                            code = ch.x;
+                        } else if (ch.y != FDD_TERMINAL) {
+                            w = cmul(w, nw[1]);
+                            slot |= bit;
+                            code = ch.y;
+                        } else {
+                            code = FDD_TERMINAL; // dead end: this row has no entry below this node
+                        }
+                    }
+                    if (code <= -2) {
+                        const int at = cnt * 32 + lane;
+                        eW[at] = w;
+                        ePack[at] = slot | (static_cast<uint32_t>(-2 - code) << 8);
+                        ++cnt;
+                    }
+                    if (sp == 0) break;
+                    --sp;
+                    const int at = (stackBase + sp) * 32 + lane;
+                    w = eW[at];
+                    const uint32_t pk = ePack[at];
+                    slot = pk >> 24;
+                    code = static_cast<int>(pk << 8) >> 8; // sign-extend the 24-bit successor code
+                }
+            }
+            for (int i = cnt; i < P; ++i) { // zero-weight padding
+                eW[i * 32 + lane] = make_double2(0.0, 0.0);
+                ePack[i * 32 + lane] = static_cast<uint32_t>(lane & (T - 1));
+            }
+        }
+        __syncwarp();
+
+        // =================== phase B: stream the sub-tiles, lane = amplitude ========================
+        for (int q = 0; q < Q; ++q) {
+            cp_async_wait<R - 1>(); // groups complete in order: the oldest one is this sub-tile
+            __syncwarp();
+            const double2* stage = ring + useSlot * T * 32;
+#pragma unroll
+            for (int j0 = 0; j0 < T; j0 += JC) {
+                double2 acc[JC];
+#pragma unroll
+                for (int jj = 0; jj < JC; ++jj) acc[jj] = make_double2(0.0, 0.0);
+                const int rowBase = (q << TB) + j0; // lane that owns output segment jj = 0
+                if (MODE != 2) {
+                    for (int i = 0; i < P; ++i) {
+#pragma unroll
+                        for (int jj = 0; jj < JC; ++jj) {
+                            const double2 w = eW[i * 32 + rowBase + jj];
+                            const uint32_t pk = ePack[i * 32 + rowBase + jj];
+                            cmac(acc[jj], w, stage[(pk & 31u) * 32 + lane]);
+                        }
+                    }
+                    if (MODE == 1) {
+                        double2 out[JC];
+#pragma unroll
+                        for (int jj = 0; jj < JC; ++jj) out[jj] = make_double2(0.0, 0.0);
+                        const int kk = subK[0];
+                        for (int k = 0; k < kk; ++k) {
+                            const double2 lw = subW[k * 32 + lane];
+                            const int lc = subCol[k * 32 + lane];
+#pragma unroll
+                            for (int jj = 0; jj < JC; ++jj) cmac(out[jj], lw, shfl2(acc[jj], lc));
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < JC; ++jj) acc[jj] = out[jj];
+                    }
+                } else {
+                    for (int i = 0; i < P; ++i) {
+#pragma unroll
+                        for (int jj = 0; jj < JC; ++jj) {
+                            const double2 w = eW[i * 32 + rowBase + jj];
+                            const uint32_t pk = ePack[i * 32 + rowBase + jj];
+                            const int sub = static_cast<int>(pk >> 8);
+                            const double2* src = stage + (pk & 31u) * 32;
+                            const int kk = subK[sub];
+                            for (int k = 0; k < kk; ++k) {
+                                const int at = (sub * p.kMax + k) * 32 + lane;
+                                cmac(acc[jj], cmul(w, subW[at]), src[subCol[at]]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int jj = 0; jj < JC; ++jj) {
+                    const uint32_t dep = __shfl_sync(0xffffffffu, myDep, rowBase + jj);
+                    if (lane < segLen) st_stream(p.z + ((static_cast<uint64_t>(base | dep)) << S) + lane, acc[jj]);
+                }
+            }
+            __syncwarp(); // every lane is done with the stage slot before it is refilled
+            useSlot = (useSlot + 1 == R) ? 0 : useSlot + 1;
+            issueNext();
+        }
+    }
+    cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -4,6 +4,8 @@
     python oracle/make_golden.py medium    # oracle/_ref/golden/<case>/ (git-ignored, travels with gpurun)
     python oracle/make_golden.py large     # samples only, minutes to tens of minutes of CPU
     python oracle/make_golden.py traces    # boundary traces of the bench circuits (no reference run)
+    python oracle/make_golden.py samples   # truncated circuits for the bounded CPU-baseline runs
+    python oracle/make_golden.py pack      # gzip the bench trace into tests/golden/traces/ (committed)
 
 Needs /root/reference (for `make -C oracle ref`) and the repo's own test circuits."""
 from __future__ import annotations
@@ -91,8 +93,40 @@ def main(argv):
         for name, (c, f) in TRACES.items():
             if not only or name in only:
                 run_case(ROOT / "oracle" / "_ref" / "traces", name, c, 8, 1, ["--trace-fuse", str(f), "--no-ref"])
+    elif what == "samples":
+        make_sample("supremacy_n26", after_switch=40)
+    elif what == "pack":
+        import gzip
+        import shutil
+        dst = ROOT / "tests" / "golden" / "traces"
+        dst.mkdir(parents=True, exist_ok=True)
+        for name in only or ["supremacy_n26_gpu"]:
+            with open(ROOT / "oracle" / "_ref" / "traces" / name / "trace.bin", "rb") as src, \
+                    gzip.GzipFile(dst / f"{name}.trace.gz", "wb", compresslevel=9, mtime=0) as out:
+                shutil.copyfileobj(src, out)
     else:
         raise SystemExit(__doc__)
+
+
+def make_sample(name: str, after_switch: int):
+    """First (switch op + 1 + after_switch) operations of a reference circuit, so the unmodified
+    reference CLI switches at the same operation and then runs a bounded array phase."""
+    import json
+    man = json.loads((ROOT / "oracle" / "_ref" / "traces" / f"{name}_ref" / "manifest.json").read_text())
+    keep = man["trace"]["switched_at_op"] + 1 + after_switch
+    out_dir = ROOT / "oracle" / "_ref" / "circuits"
+    out_dir.mkdir(parents=True, exist_ok=True)
+    lines, ops = [], 0
+    for line in (REF / "circuits" / f"{name}.qasm").read_text().splitlines():
+        is_op = "q[" in line and not line.lstrip().startswith(("//", "qreg", "creg"))
+        if is_op:
+            if ops >= keep:
+                continue
+            ops += 1
+        lines.append(line)
+    (out_dir / f"{name}_sample.qasm").write_text("\n".join(lines) + "\n")
+    (out_dir / f"{name}_sample.json").write_text(json.dumps({"source": f"{name}.qasm", "unitary_ops": ops,
+                                                            "switched_at_op": man["trace"]["switched_at_op"]}))
 
 
 if __name__ == "__main__":

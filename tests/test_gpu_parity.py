@@ -49,7 +49,7 @@ def test_convert_bit_exact(case):
     assert G.max_amp_err(re, im, G.f64(case, "kat_convert_switch1_re.f64"), G.f64(case, "kat_convert_switch1_im.f64")) < 1e-15
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("case,stem", _dmavm_kats())
 def test_dmavm_kat(case, stem, variant):
     """fdd_apply vs the reference's DDArrMultiplyIP output on the same seeded state."""
@@ -153,7 +153,7 @@ def test_gate_shapes_vs_numpy_and_oracle(n, targets, kind):
     gate = B.gate_dd(n, targets, u)
     yr, yi = B.random_state(n, rng)
     ref = B.apply_dense(n, targets, u, yr + 1j * yi)
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         with Context(n) as ctx:
             ctx.set_option("dmavm_variant", variant)
             ctx.set_state(yr, yi)
