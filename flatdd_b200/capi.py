@@ -3,6 +3,7 @@ a missing library is an ImportError-like hard failure (there is no Python/CPU fa
 from __future__ import annotations
 
 import ctypes
+import os
 from pathlib import Path
 
 import numpy as np
@@ -13,7 +14,8 @@ _PKG = Path(__file__).resolve().parent
 
 
 def library_path() -> Path:
-    return _PKG / "libflatdd_b200.so"
+    override = os.environ.get("FLATDD_B200_LIB")  # experiments only: an alternative build of the same library
+    return Path(override) if override else _PKG / "libflatdd_b200.so"
 
 
 class FlatDDError(RuntimeError):

@@ -93,6 +93,7 @@ struct fdd_ctx {
     int warpsPerCta = 0;  // 0 = chosen per launch
     int ctasPerSm = 0; // 0 = as many as shared memory allows (capped)
     int prefetch = 8;
+    int forceMode = -1;   // experiments: force the tile-kernel MODE (1, 2 or 3) where it applies
     // scratch
     double* dPartial = nullptr;
     double* dNorm = nullptr;
@@ -157,6 +158,30 @@ void uploadGate(fdd_gate* g, cudaStream_t stream) {
     g->dSubFlags = base + oF;
 }
 
+using Kernel = void (*)(const WalkParams);
+
+template <int TB> Kernel tileKernelTB(int mode, int kt) {
+    switch (mode) {
+        case 0: return dmavm_tile_kernel<TB, 0, 0>;
+        case 1: return kt == 2 ? dmavm_tile_kernel<TB, 1, 2> : (kt == 4 ? dmavm_tile_kernel<TB, 1, 4> : dmavm_tile_kernel<TB, 1, 8>);
+        case 2: return kt == 2 ? dmavm_tile_kernel<TB, 2, 2> : (kt == 4 ? dmavm_tile_kernel<TB, 2, 4> : dmavm_tile_kernel<TB, 2, 8>);
+        default:
+            return kt == 2 ? dmavm_tile_kernel<TB, 3, 2>
+                           : (kt == 4 ? dmavm_tile_kernel<TB, 3, 4> : (kt == 8 ? dmavm_tile_kernel<TB, 3, 8> : dmavm_tile_kernel<TB, 3, 0>));
+    }
+}
+
+Kernel tileKernel(int tb, int mode, int kt) {
+    switch (tb) {
+        case 0: return tileKernelTB<0>(mode, kt);
+        case 1: return tileKernelTB<1>(mode, kt);
+        case 2: return tileKernelTB<2>(mode, kt);
+        case 3: return tileKernelTB<3>(mode, kt);
+        case 4: return tileKernelTB<4>(mode, kt);
+        default: return tileKernelTB<5>(mode, kt);
+    }
+}
+
 void launchWalk(fdd_ctx* c, const fdd_gate* g) {
     const CompiledGate& h = g->host;
     if (h.n != c->n) throw std::invalid_argument("gate has " + std::to_string(h.n) + " qubits, context has " + std::to_string(c->n));
@@ -199,44 +224,44 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
         // ---- tile kernel ----------------------------------------------------------------------------
         bool allIdentity = true;
         for (uint8_t f : h.subFlags) allIdentity = allIdentity && (f & SUB_IDENTITY);
-        const int mode = allIdentity ? 0 : (h.nSub == 1 ? 1 : 2);
+        // ELL width rounded up for static unrolling; wider tables take the run-time loop of MODE 3
+        const int kt = h.kMax <= 2 ? 2 : (h.kMax <= 4 ? 4 : (h.kMax <= 8 ? 8 : 0));
+        int mode = 0;
+        if (!allIdentity) {
+            if (h.nSub == 1 && kt > 0) {
+                // instruction estimates per output segment: gather first P(8+5K), shuffle last 9P+8K
+                mode = h.maxPaths * (8 + 5 * kt) <= 9 * h.maxPaths + 8 * kt ? 1 : 2;
+            } else {
+                mode = 3;
+            }
+        }
+        if (c->forceMode >= 0 && !allIdentity && (c->forceMode == 3 || (h.nSub == 1 && kt > 0))) mode = c->forceMode;
         p.tileBits = h.tileBits;
         p.subTileBits = h.subTileBits;
         p.tileMask = h.tileMask;
         p.fillMask = h.fillMask;
         p.nTiles = p.nSeg >> h.tileBits;
         const size_t perWarpT = tileWarpSmem(p.maxPaths, p.stackCap, h.subTileBits);
+        const Kernel kernel = tileKernel(h.subTileBits, mode, kt);
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
+        // pick the CTA width that keeps the most warps resident (registers and shared memory both count)
         int bestW = 0, bestC = 0;
-        for (int ctas = 1; ctas <= 8; ++ctas) {
-            if (c->ctasPerSm > 0 && ctas > c->ctasPerSm) break;
-            const size_t avail = kSmemBudget / ctas;
-            if (avail < fixed + 1024 + perWarpT) break;
-            int w = static_cast<int>(std::min<size_t>(8, (avail - fixed - 1024) / perWarpT));
-            if (c->warpsPerCta > 0) w = std::min(w, c->warpsPerCta);
-            if (w * ctas > 32) continue; // resident-warp cap (registers: <= 128 per thread)
-            if (w * ctas > bestW * bestC) {
+        for (int w = 8; w >= 1; --w) {
+            if (c->warpsPerCta > 0 && w > c->warpsPerCta) continue;
+            const size_t smemW = fixed + static_cast<size_t>(w) * perWarpT;
+            if (smemW > kSmemBudget) continue;
+            int resident = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, w * 32, smemW));
+            if (c->ctasPerSm > 0) resident = std::min(resident, c->ctasPerSm);
+            if (resident * w > bestW * bestC) {
                 bestW = w;
-                bestC = ctas;
+                bestC = resident;
             }
         }
         if (bestW > 0) {
             const size_t smemT = fixed + static_cast<size_t>(bestW) * perWarpT;
             const uint32_t ctasWantedT = (p.nTiles + bestW - 1) / bestW;
-            using Kernel = void (*)(const WalkParams);
-            static const Kernel table[6][3] = {
-                {dmavm_tile_kernel<0, 0>, dmavm_tile_kernel<0, 1>, dmavm_tile_kernel<0, 2>},
-                {dmavm_tile_kernel<1, 0>, dmavm_tile_kernel<1, 1>, dmavm_tile_kernel<1, 2>},
-                {dmavm_tile_kernel<2, 0>, dmavm_tile_kernel<2, 1>, dmavm_tile_kernel<2, 2>},
-                {dmavm_tile_kernel<3, 0>, dmavm_tile_kernel<3, 1>, dmavm_tile_kernel<3, 2>},
-                {dmavm_tile_kernel<4, 0>, dmavm_tile_kernel<4, 1>, dmavm_tile_kernel<4, 2>},
-                {dmavm_tile_kernel<5, 0>, dmavm_tile_kernel<5, 1>, dmavm_tile_kernel<5, 2>},
-            };
-            const Kernel kernel = table[h.subTileBits][mode];
-            CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
-            int resident = bestC;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, bestW * 32, smemT));
-            resident = std::max(1, std::min(resident, bestC));
-            const int gridT = static_cast<int>(std::max<uint32_t>(1, std::min<uint32_t>(ctasWantedT, static_cast<uint32_t>(c->smCount * resident))));
+            const int gridT = static_cast<int>(std::max<uint32_t>(1, std::min<uint32_t>(ctasWantedT, static_cast<uint32_t>(c->smCount * bestC))));
             Timed t(c);
             kernel<<<gridT, bestW * 32, smemT, c->stream>>>(p);
             CUDA_TRY(cudaGetLastError());
@@ -391,6 +416,7 @@ int fdd_set_option(fdd_ctx* ctx, const char* key, long value) {
         else if (k == "warps_per_cta") ctx->warpsPerCta = static_cast<int>(value);
         else if (k == "ctas_per_sm") ctx->ctasPerSm = static_cast<int>(value);
         else if (k == "prefetch") ctx->prefetch = static_cast<int>(value);
+        else if (k == "tile_mode") ctx->forceMode = static_cast<int>(value);
         else throw std::invalid_argument("unknown option " + k);
     });
 }

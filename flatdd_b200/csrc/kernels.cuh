@@ -454,9 +454,12 @@ template <int VARIANT> __global__ void __launch_bounds__(512) dmavm_walk_kernel(
 //            tile are already in flight while phase A of that tile runs.  The T output
 //            segments of a sub-tile are accumulated together (T independent FMA chains).
 // MODE 0: the low S levels are untouched (identity sub table)      z_j = sum_i w_ji y_slot(j,i)
-// MODE 1: one sub table L for the whole gate                        z_j = L (sum_i w_ji y_slot(j,i))
-//         (L applied across lanes with warp shuffles: the operator factorises as U (x) L)
-// MODE 2: sub table depends on the path                             general ELL gather
+// MODE 1: one sub table L for the whole gate, gather first          z_j = sum_i w_ji (L y_slot(j,i))
+// MODE 2: one sub table L for the whole gate, shuffle last          z_j = L (sum_i w_ji y_slot(j,i))
+//         (the operator factorises as U (x) L; L lives in registers, KT entries per row)
+// MODE 3: sub table depends on the path, gather first               z_j = sum_i w_ji (L_sub(j,i) y_slot(j,i))
+// KT = ELL width of the sub tables rounded up to 2, 4 or 8 (static unrolling); KT = 0 (MODE 3 only)
+// reads the width at run time.  The host picks MODE 1 or 2 by instruction count.
 template <int TB> struct TileShape {
     static constexpr int T = 1 << TB;
     static constexpr int R = (16 / T) < 2 ? 2 : (16 / T);
@@ -486,7 +489,7 @@ __device__ __forceinline__ uint32_t depositAround(uint32_t x, uint32_t mask) {
     return x;
 }
 
-template <int TB, int MODE> __global__ void __launch_bounds__(256, 2) dmavm_tile_kernel(const WalkParams p) {
+template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dmavm_tile_kernel(const WalkParams p) {
     constexpr int T = TileShape<TB>::T;
     constexpr int R = TileShape<TB>::R;
     constexpr int JC = TileShape<TB>::JC;
@@ -550,6 +553,18 @@ template <int TB, int MODE> __global__ void __launch_bounds__(256, 2) dmavm_tile
                            depositBits(static_cast<uint32_t>(lane) >> TB, p.fillMask);
     const uint32_t rankBits = p.rank << upperLocalBits;
     if (warpGlobal >= p.nTiles) return;
+
+    // MODE 1/2: the single sub table lives in registers
+    constexpr int KR = (MODE == 1 || MODE == 2) ? (KT > 0 ? KT : 1) : 1;
+    double2 Lw[KR];
+    int Lc[KR];
+    if (MODE == 1 || MODE == 2) {
+#pragma unroll
+        for (int k = 0; k < KR; ++k) {
+            Lw[k] = k < p.kMax ? subW[k * 32 + lane] : make_double2(0.0, 0.0);
+            Lc[k] = k < p.kMax ? subCol[k * 32 + lane] : lane;
+        }
+    }
 
     // ---- copy pipeline state: running sub-tile counter over all warp tiles of this warp ---------
     uint32_t issueTile = warpGlobal;
@@ -649,7 +664,7 @@ template <int TB, int MODE> __global__ void __launch_bounds__(256, 2) dmavm_tile
 #pragma unroll
                 for (int jj = 0; jj < JC; ++jj) acc[jj] = make_double2(0.0, 0.0);
                 const int rowBase = (q << TB) + j0; // lane that owns output segment jj = 0
-                if (MODE != 2) {
+                if (MODE == 0 || MODE == 2) {
                     for (int i = 0; i < P; ++i) {
 #pragma unroll
                         for (int jj = 0; jj < JC; ++jj) {
@@ -658,19 +673,30 @@ template <int TB, int MODE> __global__ void __launch_bounds__(256, 2) dmavm_tile
                             cmac(acc[jj], w, stage[(pk & 31u) * 32 + lane]);
                         }
                     }
-                    if (MODE == 1) {
+                    if (MODE == 2) {
                         double2 out[JC];
 #pragma unroll
                         for (int jj = 0; jj < JC; ++jj) out[jj] = make_double2(0.0, 0.0);
-                        const int kk = subK[0];
-                        for (int k = 0; k < kk; ++k) {
-                            const double2 lw = subW[k * 32 + lane];
-                            const int lc = subCol[k * 32 + lane];
 #pragma unroll
-                            for (int jj = 0; jj < JC; ++jj) cmac(out[jj], lw, shfl2(acc[jj], lc));
+                        for (int k = 0; k < KR; ++k) {
+#pragma unroll
+                            for (int jj = 0; jj < JC; ++jj) cmac(out[jj], Lw[k], shfl2(acc[jj], Lc[k]));
                         }
 #pragma unroll
                         for (int jj = 0; jj < JC; ++jj) acc[jj] = out[jj];
+                    }
+                } else if (MODE == 1) {
+                    for (int i = 0; i < P; ++i) {
+#pragma unroll
+                        for (int jj = 0; jj < JC; ++jj) {
+                            const double2 w = eW[i * 32 + rowBase + jj];
+                            const uint32_t pk = ePack[i * 32 + rowBase + jj];
+                            const double2* src = stage + (pk & 31u) * 32;
+                            double2 t = make_double2(0.0, 0.0);
+#pragma unroll
+                            for (int k = 0; k < KR; ++k) cmac(t, Lw[k], src[Lc[k]]);
+                            cmac(acc[jj], w, t);
+                        }
                     }
                 } else {
                     for (int i = 0; i < P; ++i) {
@@ -678,13 +704,18 @@ template <int TB, int MODE> __global__ void __launch_bounds__(256, 2) dmavm_tile
                         for (int jj = 0; jj < JC; ++jj) {
                             const double2 w = eW[i * 32 + rowBase + jj];
                             const uint32_t pk = ePack[i * 32 + rowBase + jj];
-                            const int sub = static_cast<int>(pk >> 8);
                             const double2* src = stage + (pk & 31u) * 32;
-                            const int kk = subK[sub];
-                            for (int k = 0; k < kk; ++k) {
-                                const int at = (sub * p.kMax + k) * 32 + lane;
-                                cmac(acc[jj], cmul(w, subW[at]), src[subCol[at]]);
+                            const int at0 = static_cast<int>(pk >> 8) * p.kMax * 32 + lane;
+                            double2 t = make_double2(0.0, 0.0);
+                            if (KT > 0) {
+#pragma unroll
+                                for (int k = 0; k < (KT > 0 ? KT : 1); ++k) {
+                                    if (k < p.kMax) cmac(t, subW[at0 + k * 32], src[subCol[at0 + k * 32]]);
+                                }
+                            } else {
+                                for (int k = 0; k < p.kMax; ++k) cmac(t, subW[at0 + k * 32], src[subCol[at0 + k * 32]]);
                             }
+                            cmac(acc[jj], w, t);
                         }
                     }
                 }
