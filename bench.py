@@ -13,10 +13,10 @@ Metric: array-phase circuit operations per second ("gates/s"); seconds per circu
   value  kernels only, gate tables resident in HBM (compiled once), CUDA events on the library stream
   e2e    the same step through the host-buffer C-ABI: fdd_convert + fdd_apply per gate (gate
          compilation and table upload inside) + fdd_get_state into pinned host memory
-  roofline  dmavm_walk_kernel: 32 * 2^n algorithmic bytes per launch / mean launch time vs the
+  roofline  dmavm_tile_kernel: 32 * 2^n algorithmic bytes per launch / mean launch time vs the
          measured HBM copy bandwidth in MEASURED_PEAKS.json
   cpu_baseline  the unmodified reference CLI (oracle/_ref/FlatDD) on this box's host cores on a
-         bounded sample of the same circuit (first 40 array-phase operations)
+         bounded sample of the same circuit (first 160 array-phase operations)
 
 `--impl reference` times that reference CLI alone and prints the same line shape.
 """
@@ -42,7 +42,7 @@ if str(ROOT) not in sys.path:
 WORKLOAD = "supremacy_n26"
 METRIC = "array_phase_gates_per_sec"
 UNIT = "gates/s"
-SAMPLE_OPS = 40  # array-phase operations in the CPU sample circuit
+SAMPLE_OPS = 160  # array-phase operations in the CPU sample circuit (oracle/make_golden.py samples)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -174,7 +174,8 @@ def reference_arm(args) -> int:
     if rank != 0:
         return 0
     threads = host_threads()
-    for _ in range(args.warmup):
+    warmup = min(args.warmup, 1)  # a CPU process run has nothing to warm beyond the page cache
+    for _ in range(warmup):
         run_reference_once(threads)
     runs = [run_reference_once(threads) for _ in range(args.steps)]
     ops = sum(r["array_ops"] for r in runs)
@@ -184,7 +185,7 @@ def reference_arm(args) -> int:
               f"({runs[0]['launches']} fused DMAVM calls, conversion included), reference CLI --fuse 1 -t {threads}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(runs)), "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": 1e3 * secs / max(1, len(runs)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{WORKLOAD} array phase (bounded sample)", "n_qubits": 26, "fusion": "reference greedy (--fuse 1)",
                    "host_cores": os.cpu_count(), "threads": threads},
@@ -323,7 +324,7 @@ def gpu_arm(args) -> int:
             "seconds_per_circuit": t_step_ms * 1e-3,
             "convert_ms": statistics.mean(convert_ms), "dmavm_ms_per_launch": launch_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "dmavm_walk_kernel", "peak_source": peak_src, "bytes_per_launch": 32 * dim,
+                         "kernel": "dmavm_tile_kernel", "peak_source": peak_src, "bytes_per_launch": 32 * dim,
                          "convert_gbs": 16.0 * dim / (statistics.mean(convert_ms) * 1e-3) / 1e9},
             "e2e": {"value": world * array_ops / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "seconds_per_circuit": e2e_s, "steps": e2e_steps},

@@ -1,0 +1,127 @@
+// flatdd_gpu — command line front end with the flags and output contract of the reference's
+// apps/FlatDD.cpp (reference apps/FlatDD.cpp:20-146): --file --t/-t --fuse --no_cache --beta --thresh
+// --DDSIM_convert --pv --ps, the same stdout markers, the same JSON "statistics" keys and the same
+// ../../log/results/{time,state}/<name>_FlatDD.txt files.  The array phase runs on the GPU through
+// the C-ABI (include/flatdd_b200.h).  Additions: --gpu D (device), --fuse 3 (GPU cost model),
+// --bin FILE (final state as raw little-endian fp64: real array then imag array), --trace FILE
+// (also record the boundary traffic), --quiet.
+#include "cxxopts.hpp"
+#include "nlohmann/json.hpp"
+#include "reference_binding.hpp"
+
+#include <chrono>
+#include <cmath>
+#include <fstream>
+#include <iostream>
+#include <memory>
+#include <string>
+
+int main(int argc, char** argv) {
+    cxxopts::Options options("flatdd_gpu", "FlatDD with a B200 array phase");
+    // clang-format off
+    options.add_options()
+        ("h,help", "produce help message")
+        ("pv", "save the state vector")
+        ("t", "num of threads (kept for CLI compatibility; sizes the reference cost model)", cxxopts::value<unsigned int>()->default_value("16"))
+        ("ps", "print simulation stats")
+        ("file", "simulate a quantum circuit given by file", cxxopts::value<std::string>())
+        ("fuse", "0 off, 1 reference greedy, 2 DATE'19 op count, 3 GPU cost greedy", cxxopts::value<unsigned int>()->default_value("0"))
+        ("no_cache", "no cache optimization (accepted; the GPU path has no DMAV cache)")
+        ("beta", "EMA parameter (parsed and ignored like the reference: beta stays 0.9)", cxxopts::value<double>()->default_value("0.9"))
+        ("thresh", "set the threshold", cxxopts::value<double>()->default_value("2"))
+        ("DDSIM_convert", "ddsim conversion (accepted; one conversion kernel serves both)")
+        ("gpu", "CUDA device", cxxopts::value<int>()->default_value("0"))
+        ("bin", "write the final state as raw fp64 (re[], im[])", cxxopts::value<std::string>())
+        ("trace", "record the boundary traffic to this file", cxxopts::value<std::string>())
+        ("quiet", "no progress output");
+    // clang-format on
+    auto vm = options.parse(argc, argv);
+    if (vm.count("help") > 0 || vm.count("file") == 0) {
+        std::cout << options.help();
+        return vm.count("help") > 0 ? 0 : 1;
+    }
+    const auto t1 = std::chrono::high_resolution_clock::now();
+    const std::string fname = vm["file"].as<std::string>();
+    auto circuit = std::make_unique<qc::QuantumComputation>(fname);
+    const int nQubits = static_cast<int>(circuit->getNqubits());
+
+    std::unique_ptr<fddb200::GpuArrayBackend> gpu;
+    try {
+        gpu = std::make_unique<fddb200::GpuArrayBackend>(nQubits, vm["gpu"].as<int>());
+    } catch (const std::exception& e) {
+        std::cerr << "flatdd_gpu: " << e.what() << "\n";
+        return 3; // no CPU fallback
+    }
+    std::unique_ptr<fddb200::TraceRecorder> recorder;
+    std::unique_ptr<fddb200::TeeBackend> tee;
+    fddb200::ArrayBackend* backend = gpu.get();
+    if (vm.count("trace") > 0) {
+        recorder = std::make_unique<fddb200::TraceRecorder>(vm["trace"].as<std::string>(), nQubits);
+        tee = std::make_unique<fddb200::TeeBackend>(std::vector<fddb200::ArrayBackend*>{gpu.get(), recorder.get()});
+        backend = tee.get();
+    }
+    fddb200::RefGpuSwitchSimulator sim(std::move(circuit), backend);
+    sim.threshold = vm["thresh"].as<double>();
+    const auto nThread = vm["t"].as<unsigned int>();
+    sim.n_thread_exp = static_cast<unsigned int>(std::log2(nThread));
+    sim.fuse = vm["fuse"].as<unsigned int>();
+    sim.enable_cache = vm.count("no_cache") == 0;
+    sim.ddsim_convert = vm.count("DDSIM_convert") > 0;
+    sim.verbose = vm.count("quiet") == 0;
+
+    sim.simulate();
+    const auto t2 = std::chrono::high_resolution_clock::now();
+    const std::chrono::duration<float> durationSimulation = t2 - t1;
+    std::cout << "Simulation finished" << std::endl;
+
+    if (vm.count("pv") > 0 || vm.count("bin") > 0) {
+        double* re = nullptr;
+        double* im = nullptr;
+        sim.getVector(re, im); // converts the DD on the device if the switch never fired
+        const std::size_t dim = std::size_t{1} << sim.getNumberOfQubits();
+        if (vm.count("pv") > 0) {
+            std::ofstream out("../../log/results/state/" + sim.getName() + "_FlatDD.txt");
+            if (out.is_open()) {
+                for (std::size_t q = 0; q < dim; ++q) out << re[q] << " " << im[q] << std::endl;
+                std::cout << "Data saved to file." << std::endl;
+            } else {
+                std::cerr << "Failed to open the file." << std::endl;
+            }
+        }
+        if (vm.count("bin") > 0) {
+            std::ofstream out(vm["bin"].as<std::string>(), std::ios::binary);
+            out.write(reinterpret_cast<const char*>(re), static_cast<std::streamsize>(dim * sizeof(double)));
+            out.write(reinterpret_cast<const char*>(im), static_cast<std::streamsize>(dim * sizeof(double)));
+        }
+    }
+    if (recorder) recorder->close();
+
+    nlohmann::json outputObj;
+    outputObj["statistics"] = {{"simulation_time", durationSimulation.count()},
+                               {"benchmark", sim.getName()},
+                               {"n_qubits", +sim.getNumberOfQubits()},
+                               {"applied_gates", sim.getNumberOfOps()},
+                               {"DD->Array conversion", sim.getSwitchTime()},
+                               {"number of threads", nThread},
+                               // additions
+                               {"switched", sim.switched},
+                               {"switched_at_op", sim.switchedAtOp},
+                               {"unitary_gates", sim.unitaryOps},
+                               {"array_phase_gates", sim.arrayPhaseOps},
+                               {"array_phase_launches", sim.launches},
+                               {"array_phase_time", sim.arrayPhaseTime},
+                               {"gate_merging_time", sim.gateMergingTime},
+                               {"gates_per_sec_array_phase", sim.arrayPhaseTime > 0 ? static_cast<double>(sim.arrayPhaseOps) / sim.arrayPhaseTime : 0.0},
+                               {"gpu_kernel_launches", fdd_launch_count(gpu->ctx())}};
+    std::ofstream timeFile("../../log/results/time/" + sim.getName() + "_FlatDD.txt");
+    if (timeFile.is_open()) {
+        for (const auto& t : sim.getTimeRecord1()) timeFile << t << std::endl;
+        timeFile << "Switch Overhead:" << sim.getSwitchTime() << std::endl;
+        for (const auto& t : sim.getTimeRecord2()) timeFile << t << std::endl;
+        std::cout << "Time data saved to file." << std::endl;
+    } else {
+        std::cerr << "Failed to open the time file." << std::endl;
+    }
+    std::cout << std::setw(2) << outputObj << std::endl;
+    return 0;
+}

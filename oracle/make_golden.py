@@ -5,6 +5,7 @@
     python oracle/make_golden.py large     # samples only, minutes to tens of minutes of CPU
     python oracle/make_golden.py traces    # boundary traces of the bench circuits (no reference run)
     python oracle/make_golden.py samples   # truncated circuits for the bounded CPU-baseline runs
+    python oracle/make_golden.py circuits  # copy the reference's 12 circuits next to the binaries (git-ignored)
     python oracle/make_golden.py pack      # gzip the bench trace into tests/golden/traces/ (committed)
 
 Needs /root/reference (for `make -C oracle ref`) and the repo's own test circuits."""
@@ -94,7 +95,14 @@ def main(argv):
             if not only or name in only:
                 run_case(ROOT / "oracle" / "_ref" / "traces", name, c, 8, 1, ["--trace-fuse", str(f), "--no-ref"])
     elif what == "samples":
-        make_sample("supremacy_n26", after_switch=40)
+        make_sample("supremacy_n26", after_switch=160)
+    elif what == "circuits":
+        # input data for the CLI on the GPU box (which has no reference tree); git-ignored
+        import shutil
+        dst = ROOT / "oracle" / "_ref" / "circuits"
+        dst.mkdir(parents=True, exist_ok=True)
+        for q in sorted((REF / "circuits").glob("*.qasm")):
+            shutil.copyfile(q, dst / q.name)
     elif what == "pack":
         import gzip
         import shutil
