@@ -27,6 +27,7 @@ class FlatDDError(RuntimeError):
 EXPORTS = [
     "fdd_version", "fdd_last_error", "fdd_device_count", "fdd_create", "fdd_create_sharded", "fdd_destroy",
     "fdd_n_qubits", "fdd_n_local_qubits", "fdd_synchronize", "fdd_set_option", "fdd_comm_unique_id", "fdd_comm_init",
+    "fdd_exchange_qubits", "fdd_relabel_qubits", "fdd_barrier",
     "fdd_convert", "fdd_apply", "fdd_gate_compile", "fdd_gate_apply", "fdd_gate_free", "fdd_gate_info",
     "fdd_ddarr_multiply", "fdd_mac_count", "fdd_cost_ip", "fdd_cost_op1", "fdd_cost_gpu", "fdd_matdd_info", "fdd_get_state",
     "fdd_set_state", "fdd_set_zero_state", "fdd_get_amplitudes", "fdd_norm2", "fdd_state_device_ptr",
@@ -58,6 +59,9 @@ class Library:
         L.fdd_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_long]
         L.fdd_comm_unique_id.argtypes = [vp]
         L.fdd_comm_init.argtypes = [vp, vp]
+        L.fdd_exchange_qubits.argtypes = [vp, i32, i32, i32]
+        L.fdd_relabel_qubits.argtypes = [vp, i32, i32]
+        L.fdd_barrier.argtypes = [vp]
         L.fdd_convert.argtypes = [vp, ddp]
         L.fdd_apply.argtypes = [vp, ddp]
         L.fdd_gate_compile.argtypes = [vp, ddp, ctypes.POINTER(vp)]
@@ -96,6 +100,11 @@ class Library:
         n = ctypes.c_int(0)
         self.check(self.lib.fdd_device_count(ctypes.byref(n)))
         return n.value
+
+    def comm_unique_id(self) -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        self.check(self.lib.fdd_comm_unique_id(buf))
+        return buf.raw
 
     # ---- host-only cost model ---------------------------------------------------------------
     def mac_count(self, gate: FlatDD) -> int:
@@ -198,6 +207,29 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    # ---- multi-GPU -------------------------------------------------------------------------------
+    def comm_init(self, unique_id: bytes):
+        assert len(unique_id) == 128
+        buf = ctypes.create_string_buffer(unique_id, 128)
+        self.L.check(self.L.lib.fdd_comm_init(self._h, buf))
+
+    def exchange_qubits(self, global_physical_bit: int, local_physical_bit: int, method: int = 0):
+        self.L.check(self.L.lib.fdd_exchange_qubits(self._h, global_physical_bit, local_physical_bit, method))
+
+    def relabel_qubits(self, physical_bit_a: int, physical_bit_b: int):
+        self.L.check(self.L.lib.fdd_relabel_qubits(self._h, physical_bit_a, physical_bit_b))
+
+    def barrier(self):
+        self.L.check(self.L.lib.fdd_barrier(self._h))
+
+    def permutation(self) -> np.ndarray:
+        out = np.zeros(self.n_qubits, dtype=np.int32)
+        self.L.check(self.L.lib.fdd_get_permutation(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        return out
+
+    def canonicalize(self):
+        self.L.check(self.L.lib.fdd_canonicalize(self._h))
 
     def set_option(self, key: str, value: int):
         self.L.check(self.L.lib.fdd_set_option(self._h, key.encode(), int(value)))

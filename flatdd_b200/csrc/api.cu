@@ -3,6 +3,7 @@
 #include "flatdd_b200.h"
 #include "gate_compile.hpp"
 #include "kernels.cuh"
+#include "comm.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -26,6 +27,9 @@ int fail(int code, const std::string& msg) {
 struct CudaError : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
+struct CommError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
 
 #define CUDA_TRY(expr)                                                                                       \
     do {                                                                                                     \
@@ -42,6 +46,8 @@ template <class F> int guarded(F&& body) {
         return FDD_OK;
     } catch (const CudaError& e) {
         return fail(FDD_ERR_CUDA, e.what());
+    } catch (const CommError& e) {
+        return fail(FDD_ERR_COMM, e.what());
     } catch (const std::invalid_argument& e) {
         return fail(FDD_ERR_INVALID, e.what());
     } catch (const std::length_error& e) {
@@ -99,8 +105,10 @@ struct fdd_ctx {
     double* dNorm = nullptr;
     std::vector<int32_t> logicalToPhysical;
     // multi-GPU
-    const double2* peerBuf[2][kMaxPeers] = {};
-    void* comm = nullptr;
+    const double2* peerBuf[2][kMaxPeers] = {}; // state buffers of every rank (own ones included), mapped through CUDA IPC
+    ncclComm_t comm = nullptr;
+    double* dBarrier = nullptr;
+    uint64_t exchanges = 0;
 
     [[nodiscard]] uint64_t localDim() const { return uint64_t{1} << nLocal; }
 };
@@ -386,6 +394,18 @@ int fdd_destroy(fdd_ctx* ctx) {
     if (ctx == nullptr) return FDD_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream != nullptr) cudaStreamSynchronize(ctx->stream);
+    for (int b = 0; b < 2; ++b) {
+        for (int r = 0; r < kMaxPeers; ++r) {
+            if (ctx->peerBuf[b][r] != nullptr && r != ctx->rank) cudaIpcCloseMemHandle(const_cast<double2*>(ctx->peerBuf[b][r]));
+        }
+    }
+    if (ctx->comm != nullptr) {
+        try {
+            NcclApi::get().CommDestroy(ctx->comm);
+        } catch (...) {
+        }
+    }
+    cudaFree(ctx->dBarrier);
     cudaFree(ctx->buf[0]);
     cudaFree(ctx->buf[1]);
     cudaFree(ctx->dPartial);
@@ -421,8 +441,152 @@ int fdd_set_option(fdd_ctx* ctx, const char* key, long value) {
     });
 }
 
-int fdd_comm_unique_id(void* /*id128*/) { return fail(FDD_ERR_COMM, "multi-GPU exchange is not built in this revision"); }
-int fdd_comm_init(fdd_ctx* /*ctx*/, const void* /*id128*/) { return fail(FDD_ERR_COMM, "multi-GPU exchange is not built in this revision"); }
+#define NCCL_TRY(expr)                                                                                    \
+    do {                                                                                                    \
+        const ncclResult_t res__ = (expr);                                                                  \
+        if (res__ != ncclSuccess) throw CommError(std::string(#expr) + ": " + NcclApi::get().GetErrorString(res__)); \
+    } while (0)
+
+int fdd_comm_unique_id(void* id128) {
+    return guarded([&] {
+        if (id128 == nullptr) throw std::invalid_argument("id128 is null");
+        static_assert(sizeof(ncclUniqueId) == 128, "NCCL unique id size");
+        NCCL_TRY(NcclApi::get().GetUniqueId(static_cast<ncclUniqueId*>(id128)));
+    });
+}
+
+int fdd_comm_init(fdd_ctx* ctx, const void* id128) {
+    return guarded([&] {
+        if (ctx == nullptr || id128 == nullptr) throw std::invalid_argument("null argument");
+        if (ctx->world == 1) return;
+        if (ctx->comm != nullptr) throw std::logic_error("communicator already initialised");
+        useDevice(ctx);
+        NcclApi& nccl = NcclApi::get();
+        ncclUniqueId id;
+        std::memcpy(&id, id128, sizeof id);
+        NCCL_TRY(nccl.CommInitRank(&ctx->comm, ctx->world, id, ctx->rank));
+        CUDA_TRY(cudaMalloc(&ctx->dBarrier, sizeof(double)));
+        CUDA_TRY(cudaMemsetAsync(ctx->dBarrier, 0, sizeof(double), ctx->stream));
+        // trade CUDA IPC handles of both state buffers
+        constexpr size_t kH = sizeof(cudaIpcMemHandle_t);
+        std::vector<unsigned char> mineH(2 * kH), all(2 * kH * static_cast<size_t>(ctx->world));
+        for (int b = 0; b < 2; ++b) {
+            cudaIpcMemHandle_t h;
+            CUDA_TRY(cudaIpcGetMemHandle(&h, ctx->buf[b]));
+            std::memcpy(mineH.data() + b * kH, &h, kH);
+        }
+        unsigned char* dH = nullptr;
+        CUDA_TRY(cudaMalloc(&dH, all.size() + mineH.size()));
+        CUDA_TRY(cudaMemcpyAsync(dH + all.size(), mineH.data(), mineH.size(), cudaMemcpyHostToDevice, ctx->stream));
+        NCCL_TRY(nccl.AllGather(dH + all.size(), dH, mineH.size(), ncclChar, ctx->comm, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(all.data(), dH, all.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaFree(dH));
+        for (int r = 0; r < ctx->world; ++r) {
+            for (int b = 0; b < 2; ++b) {
+                if (r == ctx->rank) {
+                    ctx->peerBuf[b][r] = ctx->buf[b];
+                    continue;
+                }
+                cudaIpcMemHandle_t h;
+                std::memcpy(&h, all.data() + (static_cast<size_t>(r) * 2 + b) * kH, kH);
+                void* p = nullptr;
+                CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+                ctx->peerBuf[b][r] = static_cast<const double2*>(p);
+            }
+        }
+    });
+}
+
+namespace {
+
+void streamBarrier(fdd_ctx* c) {
+    // a one-element all-reduce on the context's stream: no rank passes it before every rank got here
+    NCCL_TRY(NcclApi::get().AllReduce(c->dBarrier, c->dBarrier, 1, ncclDouble, ncclSum, c->comm, c->stream));
+}
+
+void swapLocalBits(fdd_ctx* c, int a, int b) {
+    if (a == b) return;
+    const uint64_t dim = c->localDim();
+    swap_local_bits_kernel<<<gridFor(c, dim, 256), 256, 0, c->stream>>>(c->buf[c->cur], c->buf[c->cur ^ 1], dim, std::min(a, b), std::max(a, b));
+    CUDA_TRY(cudaGetLastError());
+    c->launches++;
+    c->cur ^= 1;
+}
+
+// physical SWAP(pg, pl) of one global and one local index bit
+void exchangeBits(fdd_ctx* c, int pg, int pl, int method) {
+    if (c->comm == nullptr) throw std::logic_error("shards are not connected: call fdd_comm_init first");
+    const int gbit = pg - c->nLocal;
+    const int partner = c->rank ^ (1 << gbit);
+    const int myBit = (c->rank >> gbit) & 1;
+    const uint64_t dim = c->localDim();
+    if (method == 0) {
+        streamBarrier(c); // every rank has finished writing its current buffer
+        const int grid = c->smCount * 8;
+        exchange_p2p_kernel<<<grid, 256, 0, c->stream>>>(c->buf[c->cur], c->peerBuf[c->cur][partner], c->buf[c->cur ^ 1], dim, pl, myBit);
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+        streamBarrier(c); // nobody overwrites a buffer a peer may still be reading
+        c->cur ^= 1;
+    } else {
+        const int top = c->nLocal - 1;
+        swapLocalBits(c, pl, top);
+        const uint64_t half = dim >> 1;
+        const uint64_t keepOff = myBit ? half : 0, sendOff = myBit ? 0 : half;
+        NcclApi& nccl = NcclApi::get();
+        NCCL_TRY(nccl.GroupStart());
+        NCCL_TRY(nccl.Send(c->buf[c->cur] + sendOff, half * 2, ncclDouble, partner, c->comm, c->stream));
+        NCCL_TRY(nccl.Recv(c->buf[c->cur ^ 1] + sendOff, half * 2, ncclDouble, partner, c->comm, c->stream));
+        NCCL_TRY(nccl.GroupEnd());
+        CUDA_TRY(cudaMemcpyAsync(c->buf[c->cur ^ 1] + keepOff, c->buf[c->cur] + keepOff, half * sizeof(double2), cudaMemcpyDeviceToDevice, c->stream));
+        c->cur ^= 1;
+        swapLocalBits(c, pl, top);
+    }
+    c->exchanges++;
+}
+
+void swapPermutationEntries(fdd_ctx* c, int pa, int pb) {
+    for (auto& p : c->logicalToPhysical) {
+        if (p == pa) p = pb;
+        else if (p == pb) p = pa;
+    }
+}
+
+} // namespace
+
+int fdd_exchange_qubits(fdd_ctx* ctx, int global_physical_bit, int local_physical_bit, int method) {
+    return guarded([&] {
+        if (ctx == nullptr) throw std::invalid_argument("ctx is null");
+        if (ctx->world == 1) throw std::logic_error("context is not sharded");
+        if (global_physical_bit < ctx->nLocal || global_physical_bit >= ctx->n) throw std::invalid_argument("first argument is not a global physical bit");
+        if (local_physical_bit < 0 || local_physical_bit >= ctx->nLocal) throw std::invalid_argument("second argument is not a local physical bit");
+        if (!ctx->hasState) throw std::logic_error("no state");
+        useDevice(ctx);
+        Timed t(ctx);
+        exchangeBits(ctx, global_physical_bit, local_physical_bit, method);
+        swapPermutationEntries(ctx, global_physical_bit, local_physical_bit);
+    });
+}
+
+int fdd_relabel_qubits(fdd_ctx* ctx, int physical_bit_a, int physical_bit_b) {
+    return guarded([&] {
+        if (ctx == nullptr) throw std::invalid_argument("ctx is null");
+        if (physical_bit_a < 0 || physical_bit_a >= ctx->n || physical_bit_b < 0 || physical_bit_b >= ctx->n) throw std::invalid_argument("physical bit out of range");
+        swapPermutationEntries(ctx, physical_bit_a, physical_bit_b);
+    });
+}
+
+int fdd_barrier(fdd_ctx* ctx) {
+    return guarded([&] {
+        if (ctx == nullptr) throw std::invalid_argument("ctx is null");
+        if (ctx->world == 1) return;
+        if (ctx->comm == nullptr) throw std::logic_error("shards are not connected: call fdd_comm_init first");
+        useDevice(ctx);
+        streamBarrier(ctx);
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    });
+}
 
 int fdd_convert(fdd_ctx* ctx, const fdd_vecdd* dd) {
     return guarded([&] {
@@ -520,6 +684,7 @@ static long gateFact(const CompiledGate& h, const std::string& k) {
     if (k == "top_level") return h.topLevel;
     if (k == "upper_depth") return h.upperDepth;
     if (k == "stack_cap") return h.stackCap;
+    if (k == "non_diag_mask") return static_cast<long>(h.nonDiagMask);
     if (k == "nnz") return static_cast<long>(h.nnz);
     if (k == "tileable") return h.tileable ? 1 : 0;
     if (k == "sub_tile_bits") return h.subTileBits;
@@ -691,11 +856,28 @@ int fdd_get_permutation(const fdd_ctx* ctx, int32_t* logical_to_physical) {
 }
 
 int fdd_canonicalize(fdd_ctx* ctx) {
-    if (ctx == nullptr) return fail(FDD_ERR_INVALID, "ctx is null");
-    for (int q = 0; q < ctx->n; ++q) {
-        if (ctx->logicalToPhysical[static_cast<size_t>(q)] != q) return fail(FDD_ERR_COMM, "qubit remap present but exchange is not built in this revision");
-    }
-    return FDD_OK;
+    return guarded([&] {
+        if (ctx == nullptr) throw std::invalid_argument("ctx is null");
+        useDevice(ctx);
+        auto& l2p = ctx->logicalToPhysical;
+        // bring logical qubit p to physical position p, highest position first
+        for (int p = ctx->n - 1; p >= 0; --p) {
+            const int c = l2p[static_cast<size_t>(p)]; // where logical p sits now
+            if (c == p) continue;
+            const bool pGlobal = p >= ctx->nLocal, cGlobal = c >= ctx->nLocal;
+            if (!pGlobal && !cGlobal) {
+                swapLocalBits(ctx, p, c);
+            } else if (pGlobal != cGlobal) {
+                exchangeBits(ctx, pGlobal ? p : c, pGlobal ? c : p, 0);
+            } else {
+                // both global: route through local bit 0 (three exchanges)
+                exchangeBits(ctx, p, 0, 0);
+                exchangeBits(ctx, c, 0, 0);
+                exchangeBits(ctx, p, 0, 0);
+            }
+            swapPermutationEntries(ctx, p, c);
+        }
+    });
 }
 
 int fdd_last_kernel_ms(fdd_ctx* ctx, float* ms) {

@@ -1,0 +1,102 @@
+// comm.cuh — multi-GPU plumbing of the sharded state: one process per GPU.
+//   * NCCL (loaded with dlopen so the library has no link-time dependency and shares the NCCL
+//     instance of the hosting process, e.g. torch's) for the rendezvous, barriers in stream
+//     order and the send/recv exchange path;
+//   * CUDA IPC so that every rank maps the state buffers of all peers: the P2P exchange kernel
+//     reads the partner's half shard straight over NVLink (NVSwitch: full bandwidth to any peer).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <stdexcept>
+#include <string>
+
+namespace fddb200 {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+
+    static NcclApi& get() {
+        static NcclApi api = load();
+        return api;
+    }
+
+private:
+    template <class F> static void sym(void* h, F& f, const char* name) {
+        f = reinterpret_cast<F>(dlsym(h, name));
+        if (f == nullptr) throw std::runtime_error(std::string("NCCL symbol missing: ") + name);
+    }
+    static NcclApi load() {
+        NcclApi a;
+        // RTLD_NOLOAD first: reuse the instance the process already has (same SONAME)
+        a.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+        if (a.handle == nullptr) a.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (a.handle == nullptr) a.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (a.handle == nullptr) throw std::runtime_error(std::string("cannot load NCCL: ") + dlerror());
+        sym(a.handle, a.GetUniqueId, "ncclGetUniqueId");
+        sym(a.handle, a.CommInitRank, "ncclCommInitRank");
+        sym(a.handle, a.CommDestroy, "ncclCommDestroy");
+        sym(a.handle, a.GetErrorString, "ncclGetErrorString");
+        sym(a.handle, a.AllReduce, "ncclAllReduce");
+        sym(a.handle, a.AllGather, "ncclAllGather");
+        sym(a.handle, a.Send, "ncclSend");
+        sym(a.handle, a.Recv, "ncclRecv");
+        sym(a.handle, a.GroupStart, "ncclGroupStart");
+        sym(a.handle, a.GroupEnd, "ncclGroupEnd");
+        return a;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// exchange kernels
+// ------------------------------------------------------------------------------------------------
+// SWAP(global physical bit, local physical bit `pl`) seen from one shard whose global bit has the
+// value `myBit`: the half with bit pl == myBit stays, the other half is replaced by the
+// partner's half with bit pl == myBit.  Out of place (mine -> out) so that the partner can read
+// `mine` at the same time; half of the reads cross NVLink, 16-byte vectors, 4 in flight per thread.
+__global__ void __launch_bounds__(256) exchange_p2p_kernel(const double2* __restrict__ mine, const double2* __restrict__ partner,
+                                                           double2* __restrict__ out, uint64_t n, int pl, int myBit) {
+    const uint64_t flip = uint64_t{1} << pl;
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        double2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t j = i + u * stride;
+            const bool keep = static_cast<int>((j >> pl) & 1ULL) == myBit;
+            v[u] = keep ? mine[j] : partner[j ^ flip];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) out[i + u * stride] = v[u];
+    }
+    for (; i < n; i += stride) {
+        const bool keep = static_cast<int>((i >> pl) & 1ULL) == myBit;
+        out[i] = keep ? mine[i] : partner[i ^ flip];
+    }
+}
+
+// local SWAP of two physical bits (a < b), out of place; used by the NCCL path to bring `pl` to the top
+__global__ void __launch_bounds__(256) swap_local_bits_kernel(const double2* __restrict__ in, double2* __restrict__ out, uint64_t n,
+                                                              int a, int b) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t ba = (i >> a) & 1ULL, bb = (i >> b) & 1ULL;
+        const uint64_t j = (ba != bb) ? (i ^ ((uint64_t{1} << a) | (uint64_t{1} << b))) : i;
+        out[i] = in[j];
+    }
+}
+
+} // namespace fddb200

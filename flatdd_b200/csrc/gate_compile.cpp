@@ -369,6 +369,9 @@ CompiledGate compileGate(const fdd_matdd& g, int nLocal) {
             if (!isZero(W(u, 1)) || !isZero(W(u, 2))) nonDiag |= uint64_t{1} << (g.level[u] - S);
         }
         out.nonDiagUpper = __builtin_popcountll(nonDiag);
+        for (int32_t u = 0; u < g.n_nodes; ++u) {
+            if (reach[static_cast<std::size_t>(u)] && (!isZero(W(u, 1)) || !isZero(W(u, 2)))) out.nonDiagMask |= uint64_t{1} << g.level[u];
+        }
         const int localSegBits = std::max(0, nLocal - S);
         out.tileBits = std::min(5, localSegBits);
         const bool allLocal = (nonDiag >> localSegBits) == 0;

@@ -70,6 +70,7 @@ struct CompiledGate {
     uint32_t tileMask = 0; // index bits of the non-diagonal upper levels (a sub-tile is closed under the gate)
     uint32_t fillMask = 0; // lowest free index bits that complete the warp tile
     int nonDiagUpper = 0; // upper levels with an off-diagonal successor
+    uint64_t nonDiagMask = 0; // bit v set when level v has an off-diagonal successor (all levels)
 };
 
 // Throws std::runtime_error with a message on malformed input.

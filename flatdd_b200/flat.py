@@ -128,9 +128,10 @@ def read_flat(path) -> FlatDD:
 
 @dataclass
 class TraceRecord:
-    kind: int  # 1 = convert this vector DD, 2 = apply this matrix DD
+    kind: int  # 1 = convert, 2 = apply, 3 = exchange (global, local) physical bits, 4 = relabel two physical bits
     n_original_gates: int
-    dd: FlatDD
+    dd: FlatDD | None
+    exchange: tuple | None = None  # (global physical bit, local physical bit) for kind 3
 
 
 def read_trace(path) -> tuple[int, List[TraceRecord]]:
@@ -146,6 +147,11 @@ def read_trace(path) -> tuple[int, List[TraceRecord]]:
         off += 16
         rw = np.frombuffer(buf, dtype="<f8", count=2, offset=off).copy()
         off += 16
+        if kind in (3, 4):  # exchange / relabel of two physical bits
+            records.append(TraceRecord(kind, 0, None, (n_nodes, root)))
+            continue
+        if kind == 5:  # meta: world size the schedule was made for
+            continue
         radix = 2 if kind == 1 else 4
         level, child, weight, off = _parse_tables(buf, off, n_nodes, radix)
         records.append(TraceRecord(kind, n_orig, FlatDD(n_qubits, radix, root, rw, level, child, weight)))

@@ -31,9 +31,17 @@ public:
     // one DMAVM (reference: DDArrMultiplyIP / DDArrMultiplyOP); `nOriginalGates` = how many
     // circuit operations were fused into this matrix (bookkeeping only)
     virtual void apply(const FlatMatDD& gate, int nOriginalGates) = 0;
-    // copy the current state into SoA arrays of 2^n doubles (reference: getVector)
+    // copy the current state into SoA arrays of 2^n_local doubles (reference: getVector)
     virtual void getState(double* real, double* imag) = 0;
     virtual void synchronize() {}
+    // sharded states only: SWAP of a global and a local physical index bit (half-shard exchange),
+    // and the undo of all such swaps so that shard r again holds the amplitudes with top bits r
+    virtual void exchange(int /*globalPhysicalBit*/, int /*localPhysicalBit*/) {
+        throw std::runtime_error("this backend holds an unsharded state");
+    }
+    // the logical qubits at two physical bits trade names (absorbed SWAP gate); no data moves
+    virtual void relabel(int /*physicalBitA*/, int /*physicalBitB*/) {}
+    virtual void canonicalize() {}
 };
 
 inline void fddCheck(int rc, const char* what) {
@@ -45,6 +53,15 @@ inline void fddCheck(int rc, const char* what) {
 class GpuArrayBackend final : public ArrayBackend {
 public:
     GpuArrayBackend(int nQubits, int device = 0) { fddCheck(fdd_create(nQubits, device, &ctx_), "fdd_create"); }
+    // one shard of a state distributed over `worldSize` processes; `ncclUniqueId128` comes from
+    // fdd_comm_unique_id on rank 0 and reaches the other ranks through the launcher
+    GpuArrayBackend(int nQubits, int device, int rank, int worldSize, const void* ncclUniqueId128, int exchangeMethod = 0)
+        : exchangeMethod_(exchangeMethod) {
+        fddCheck(fdd_create_sharded(nQubits, device, rank, worldSize, &ctx_), "fdd_create_sharded");
+        if (worldSize > 1) {
+            fddCheck(fdd_comm_init(ctx_, ncclUniqueId128), "fdd_comm_init");
+        }
+    }
     GpuArrayBackend(const GpuArrayBackend&) = delete;
     GpuArrayBackend& operator=(const GpuArrayBackend&) = delete;
     ~GpuArrayBackend() override {
@@ -62,10 +79,16 @@ public:
     }
     void getState(double* real, double* imag) override { fddCheck(fdd_get_state(ctx_, real, imag), "fdd_get_state"); }
     void synchronize() override { fddCheck(fdd_synchronize(ctx_), "fdd_synchronize"); }
+    void exchange(int globalPhysicalBit, int localPhysicalBit) override {
+        fddCheck(fdd_exchange_qubits(ctx_, globalPhysicalBit, localPhysicalBit, exchangeMethod_), "fdd_exchange_qubits");
+    }
+    void relabel(int a, int b) override { fddCheck(fdd_relabel_qubits(ctx_, a, b), "fdd_relabel_qubits"); }
+    void canonicalize() override { fddCheck(fdd_canonicalize(ctx_), "fdd_canonicalize"); }
     [[nodiscard]] fdd_ctx* ctx() const { return ctx_; }
 
 private:
     fdd_ctx* ctx_ = nullptr;
+    int exchangeMethod_ = 0;
 };
 
 // Binary trace, little endian:
@@ -73,6 +96,9 @@ private:
 //   records: int32 kind (1 = vector DD to convert, 2 = matrix DD to apply), int32 n_nodes,
 //            int32 root, int32 n_original_gates, double root_weight[2],
 //            int32 level[n_nodes], int32 child[R*n_nodes], double weight[2*R*n_nodes]   (R = 2 or 4)
+//            kind 3 = exchange: the n_nodes field holds the global physical bit, the root field the
+//            local physical bit, no tables; kind 4 = relabel (two physical bits, same fields);
+//            kind 5 = meta: the n_nodes field holds the world size
 class TraceRecorder final : public ArrayBackend {
 public:
     TraceRecorder(const std::string& path, int nQubits) : file_(std::fopen(path.c_str(), "wb")) {
@@ -91,6 +117,9 @@ public:
     void convert(const FlatVecDD& dd) override { record<2>(1, dd, 0); }
     void apply(const FlatMatDD& gate, int nOriginalGates) override { record<4>(2, gate, nOriginalGates); }
     void getState(double*, double*) override { throw std::runtime_error("TraceRecorder holds no state"); }
+    void exchange(int globalPhysicalBit, int localPhysicalBit) override { marker(3, globalPhysicalBit, localPhysicalBit); }
+    void relabel(int a, int b) override { marker(4, a, b); }
+    void setWorldSize(int worldSize) { marker(5, worldSize, 0); }
     void close() {
         if (file_ != nullptr) {
             std::fseek(file_, 12, SEEK_SET);
@@ -106,6 +135,13 @@ private:
         if (bytes != 0 && std::fwrite(p, 1, bytes, file_) != bytes) {
             throw std::runtime_error("TraceRecorder: short write");
         }
+    }
+    void marker(int32_t kind, int32_t a, int32_t b) {
+        const int32_t head[4] = {kind, a, b, 0};
+        const double zero[2] = {0.0, 0.0};
+        put(head, sizeof head);
+        put(zero, sizeof zero);
+        ++records_;
     }
     template <int R> void record(int32_t kind, const FlatDD<R>& dd, int32_t nOriginal) {
         const int32_t head[4] = {kind, dd.nNodes(), dd.root, nOriginal};
@@ -138,6 +174,21 @@ public:
     void synchronize() override {
         for (auto* s : sinks_) {
             s->synchronize();
+        }
+    }
+    void exchange(int globalPhysicalBit, int localPhysicalBit) override {
+        for (auto* s : sinks_) {
+            s->exchange(globalPhysicalBit, localPhysicalBit);
+        }
+    }
+    void relabel(int a, int b) override {
+        for (auto* s : sinks_) {
+            s->relabel(a, b);
+        }
+    }
+    void canonicalize() override {
+        for (auto* s : sinks_) {
+            s->canonicalize();
         }
     }
 

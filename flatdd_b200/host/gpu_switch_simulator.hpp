@@ -121,6 +121,16 @@ public:
     double threshold = 3.5;
 
     // ---- additions ---------------------------------------------------------------------------
+    // > 1: this process simulates one shard of a state distributed over `worldSize` GPUs by its
+    // top log2(worldSize) physical qubits.  Every rank runs this same driver on the same circuit and
+    // takes the same decisions; only the backend differs by rank.  Gates must be non-diagonal on local
+    // physical qubits only, so before such a gate the driver swaps the global qubit with a local one
+    // (ArrayBackend::exchange) and tracks the logical->physical map the way the reference tracks
+    // layouts (qc::Permutation, include/Permutation.hpp:9-25); gate DDs are then built in physical
+    // order with dd::getDD(op, dd, permutation) (include/dd/Operations.hpp:591-678).
+    int worldSize = 1;
+    std::size_t exchanges = 0;     // half-shard exchanges issued
+    std::size_t lookahead = 4096;  // operations scanned ahead when choosing the local qubit to evict
     FusionPolicy policy{};
     long switchedAtOp = -1;        // index printed as "Switching at instr."
     std::size_t unitaryOps = 0;    // unitary operations seen (incl. barriers)
@@ -171,6 +181,97 @@ private:
         switchTime = since(t0);
     }
 
+    // ---- sharded mode -------------------------------------------------------------------------
+    using Perm = typename DdOps::Permutation;
+    [[nodiscard]] int nLocal() const {
+        int bits = 0;
+        while ((1 << bits) < worldSize) ++bits;
+        return nq() - bits;
+    }
+    void initPermutation() {
+        perm.clear();
+        nonDiag.clear();
+        if (worldSize <= 1) return;
+        for (int q = 0; q < nq(); ++q) perm[static_cast<typename Perm::key_type>(q)] = static_cast<typename Perm::mapped_type>(q);
+        for (const auto& op : qc->ops) nonDiag.push_back(DdOps::nonDiagonalQubits(*op));
+    }
+    // one layout change: exchange == true moves data (half-shard exchange), false only renames
+    struct LayoutStep {
+        bool exchange;
+        int a, b;
+    };
+    // `deferred`: when a schedule is being built the layout steps are queued there (they must run in
+    // schedule order, after the gates scheduled before them), otherwise they go to the backend now
+    MEdge gateFor(const typename Qc::iterator::value_type::element_type* op, std::vector<LayoutStep>* deferred = nullptr) {
+        if (worldSize <= 1) return DdOps::getDD(op, dd);
+        if (DdOps::isRelabelSwap(*op)) {
+            // an uncontrolled SWAP is absorbed into the layout: no launch, no data movement
+            const auto t = DdOps::swapTargets(*op);
+            auto& pa = perm[static_cast<typename Perm::key_type>(t.first)];
+            auto& pb = perm[static_cast<typename Perm::key_type>(t.second)];
+            if (deferred != nullptr) {
+                deferred->push_back({false, static_cast<int>(pa), static_cast<int>(pb)});
+            } else {
+                backend->relabel(static_cast<int>(pa), static_cast<int>(pb));
+            }
+            std::swap(pa, pb);
+            return dd->makeIdent(qc->getNqubits());
+        }
+        return DdOps::getDD(op, dd, perm);
+    }
+    void runLayoutStep(const LayoutStep& st) {
+        if (st.exchange) {
+            doExchange(st.a, st.b);
+        } else {
+            backend->relabel(st.a, st.b);
+        }
+    }
+    // Exchanges (global physical bit, local physical bit) needed before operation `k`; updates perm.
+    // Victim = the local qubit whose next non-diagonal use lies furthest ahead (Belady).
+    std::vector<std::pair<int, int>> planExchanges(std::size_t k) {
+        std::vector<std::pair<int, int>> plan;
+        if (worldSize <= 1 || DdOps::isRelabelSwap(*qc->ops[k])) return plan;
+        const int local = nLocal();
+        const auto& need = nonDiag[k];
+        for (int q : need) {
+            const int pq = static_cast<int>(perm[static_cast<typename Perm::key_type>(q)]);
+            if (pq < local) continue;
+            int victim = -1;
+            std::size_t victimUse = 0;
+            int victimPos = -1;
+            for (int cand = 0; cand < nq(); ++cand) {
+                const int pc = static_cast<int>(perm[static_cast<typename Perm::key_type>(cand)]);
+                if (pc >= local) continue;
+                bool busy = false;
+                for (int x : need) busy = busy || x == cand;
+                if (busy) continue;
+                std::size_t use = k + 1 + lookahead; // "never" within the window
+                for (std::size_t j = k + 1; j < qc->ops.size() && j <= k + lookahead; ++j) {
+                    bool hit = false;
+                    for (int x : nonDiag[j]) hit = hit || x == cand;
+                    if (hit) {
+                        use = j;
+                        break;
+                    }
+                }
+                if (victim < 0 || use > victimUse || (use == victimUse && pc > victimPos)) {
+                    victim = cand;
+                    victimUse = use;
+                    victimPos = pc;
+                }
+            }
+            if (victim < 0) throw std::runtime_error("no local qubit available for the exchange (gate touches too many qubits)");
+            plan.emplace_back(pq, victimPos);
+            std::swap(perm[static_cast<typename Perm::key_type>(q)], perm[static_cast<typename Perm::key_type>(victim)]);
+        }
+        return plan;
+    }
+    void doExchange(int pg, int pl) {
+        backend->exchange(pg, pl);
+        ++exchanges;
+        hostValid = false;
+    }
+
     void launch(const MEdge& gate, int nOriginal) {
         const auto flat = flatten<4, MEdge, WeightTraits>(gate, nq());
         backend->apply(flat, nOriginal);
@@ -191,6 +292,7 @@ private:
         rootEdge = dd->makeZeroState(n);
         dd->incRef(rootEdge);
         EMA_v = static_cast<double>(n);
+        initPermutation();
         if (!enable_switch) {
             runAllArray(ignoreNonUnitaries);
         } else if (fuse == 0) {
@@ -205,7 +307,8 @@ private:
     void runPerGate(bool ignoreNonUnitaries) {
         std::size_t opNum = 0;
         Clock::time_point arrayStart{};
-        for (auto& op : *qc) {
+        for (std::size_t k = 0; k < qc->ops.size(); ++k) {
+            auto& op = qc->ops[k];
             if (skipped(op, ignoreNonUnitaries)) {
                 continue;
             }
@@ -213,11 +316,16 @@ private:
                 std::cout << "[Instruction Count]  " << opNum << std::endl;
             }
             const auto t0 = Clock::now();
-            auto gate = DdOps::getDD(op.get(), dd);
             if (!switched) {
-                multiplyIntoRoot(gate);
+                multiplyIntoRoot(DdOps::getDD(op.get(), dd));
             } else {
-                launch(gate, 1);
+                for (const auto& ex : planExchanges(k)) doExchange(ex.first, ex.second);
+                auto gate = gateFor(op.get());
+                if (!isIdentity(gate)) {
+                    launch(gate, 1);
+                } else {
+                    ++arrayPhaseOps;
+                }
             }
             dd->garbageCollect();
             (switched ? timeRecord2 : timeRecord1).push_back(since(t0));
@@ -242,6 +350,19 @@ private:
         std::vector<MEdge> gates;
         std::vector<int> originals; // circuit operations per fused gate
         std::vector<bool> useCache; // the reference's in_or_out flag (statistics only)
+        // sharded mode: layout steps to run BEFORE gate i (index into `gates`), in order
+        std::vector<std::vector<LayoutStep>> layoutBefore;
+        void push(const MEdge& g, int count, bool cache) {
+            gates.push_back(g);
+            originals.push_back(count);
+            useCache.push_back(cache);
+            layoutBefore.emplace_back(std::move(pending));
+            pending.clear();
+        }
+        void queueExchanges(const std::vector<std::pair<int, int>>& plan) {
+            for (const auto& ex : plan) pending.push_back({true, ex.first, ex.second});
+        }
+        std::vector<LayoutStep> pending;
     };
 
     // cost of one gate under the active policy
@@ -293,13 +414,19 @@ private:
             }
             std::size_t merged = 0;
             for (std::size_t k = first; k < ops.size() && !ops[k]->isNonUnitaryOperation(); ++k) {
-                auto next = DdOps::getDD(ops[k].get(), dd);
+                auto plan = planExchanges(k);
+                if (!plan.empty()) { // a remap ends the group: its gates were built for the old layout
+                    s.push(current, currentCount, false);
+                    s.queueExchanges(plan);
+                    current = dd->makeIdent(qc->getNqubits());
+                    currentCount = 0;
+                    merged = 0;
+                }
+                auto next = gateFor(ops[k].get(), &s.pending);
                 auto candidate = dd->multiply(next, current);
                 ++merged;
                 if (merged > 5) {
-                    s.gates.push_back(current);
-                    s.originals.push_back(currentCount);
-                    s.useCache.push_back(false);
+                    s.push(current, currentCount, false);
                     current = next;
                     currentCount = 1;
                     merged = 0;
@@ -308,9 +435,7 @@ private:
                     ++currentCount;
                 }
             }
-            s.gates.push_back(current);
-            s.originals.push_back(currentCount);
-            s.useCache.push_back(false);
+            s.push(current, currentCount, false);
             return s;
         }
         if (verbose) {
@@ -321,15 +446,24 @@ private:
         std::size_t totalComp = 0;
         std::size_t savedComp = 0;
         for (std::size_t k = first; k < ops.size() && !ops[k]->isNonUnitaryOperation(); ++k) {
-            auto next = DdOps::getDD(ops[k].get(), dd);
+            auto plan = planExchanges(k);
+            if (!plan.empty()) { // a remap ends the group: its gates were built for the old layout
+                s.push(current, currentCount, held.cache);
+                totalComp += held.ip;
+                savedComp += held.ip - held.value;
+                s.queueExchanges(plan);
+                current = dd->makeIdent(qc->getNqubits());
+                currentCount = 0;
+                held = Cost{};
+                macMap.clear();
+            }
+            auto next = gateFor(ops[k].get(), &s.pending);
             const Cost nextCost = fuse == 1 ? referenceCost(next, macMap, nDim) : gpuCost(next);
             auto candidate = dd->multiply(next, current);
             const Cost mergedCost = fuse == 1 ? referenceCost(candidate, macMap, nDim) : gpuCost(candidate);
             const bool lastOp = k == ops.size() - 1 || ops[k + 1]->isNonUnitaryOperation();
             if (held.value + nextCost.value < mergedCost.value || lastOp) {
-                s.gates.push_back(current);
-                s.originals.push_back(currentCount);
-                s.useCache.push_back(held.cache);
+                s.push(current, currentCount, held.cache);
                 totalComp += held.ip;
                 savedComp += held.ip - held.value;
                 held = nextCost;
@@ -342,9 +476,7 @@ private:
                 held = mergedCost;
             }
         }
-        s.gates.push_back(current);
-        s.originals.push_back(currentCount);
-        s.useCache.push_back(false);
+        s.push(current, currentCount, false);
         totalComp += held.ip;
         if (verbose) {
             std::cout << "Cost: " << totalComp - savedComp << std::endl;
@@ -362,6 +494,7 @@ private:
         const auto t0 = Clock::now();
         for (std::size_t i = 0; i < s.gates.size(); ++i) {
             const auto tg = Clock::now();
+            for (const auto& st : s.layoutBefore[i]) runLayoutStep(st);
             if (!isIdentity(s.gates[i])) {
                 launch(s.gates[i], s.originals[i]);
             } else {
@@ -432,11 +565,13 @@ private:
         if (fuse == 0) {
             std::size_t opNum = 0;
             const auto t0 = Clock::now();
-            for (auto& op : *qc) {
+            for (std::size_t k = 0; k < qc->ops.size(); ++k) {
+                auto& op = qc->ops[k];
                 if (skipped(op, ignoreNonUnitaries)) {
                     continue;
                 }
-                auto gate = DdOps::getDD(op.get(), dd);
+                for (const auto& ex : planExchanges(k)) doExchange(ex.first, ex.second);
+                auto gate = gateFor(op.get());
                 if (!isIdentity(gate)) {
                     launch(gate, 1);
                 } else {
@@ -483,11 +618,15 @@ private:
         if (hostValid) {
             return;
         }
-        const std::size_t dim = std::size_t{1} << qc->getNqubits();
+        const std::size_t dim = std::size_t{1} << (worldSize > 1 ? nLocal() : nq()); // a shard in sharded mode
         hostReal.assign(dim, 0.0);
         hostImag.assign(dim, 0.0);
         if (!onDevice) {
             getVectorFromDD();
+        }
+        if (worldSize > 1) {
+            backend->canonicalize(); // undo the qubit remap: shard r = amplitudes with top index bits r
+            initPermutation();
         }
         backend->getState(hostReal.data(), hostImag.data());
         hostValid = true;
@@ -495,6 +634,8 @@ private:
 
     std::unique_ptr<Qc> qc;
     ArrayBackend* backend;
+    Perm perm;                             // logical -> physical qubit (sharded mode only)
+    std::vector<std::vector<int>> nonDiag; // per operation: logical qubits it is non-diagonal on
     double pendingEma = 0.0;
     bool onDevice = false;
     bool hostValid = false;

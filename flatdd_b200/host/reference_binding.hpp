@@ -25,7 +25,38 @@ struct RefWeightTraits {
 using RefPackage = dd::SwitchPackage<dd::DDPackageConfig>;
 
 struct RefDdOps {
+    using Permutation = qc::Permutation;
     static qc::MatrixDD getDD(const qc::Operation* op, std::unique_ptr<RefPackage>& pkg) { return dd::getDD(op, pkg); }
+    // gate DD with its qubits relabelled logical -> physical (include/dd/Operations.hpp:591-678)
+    static qc::MatrixDD getDD(const qc::Operation* op, std::unique_ptr<RefPackage>& pkg, Permutation& perm) {
+        return dd::getDD(op, pkg, perm);
+    }
+    // with a permutation the reference turns an uncontrolled SWAP into a relabelling (Operations.hpp:611-620)
+    static bool isRelabelSwap(const qc::Operation& op) { return op.getType() == qc::SWAP && !op.isControlled(); }
+    static std::pair<int, int> swapTargets(const qc::Operation& op) {
+        return {static_cast<int>(op.getTargets()[0]), static_cast<int>(op.getTargets()[1])};
+    }
+    // logical qubits on which the operation is NOT diagonal in the computational basis; controls are
+    // always diagonal, targets are unless the gate type is a phase-type gate
+    static std::vector<int> nonDiagonalQubits(const qc::Operation& op) {
+        std::vector<int> out;
+        if (op.isNonUnitaryOperation()) return out;
+        if (const auto* compound = dynamic_cast<const qc::CompoundOperation*>(&op)) {
+            for (const auto& sub : *compound) {
+                for (int q : nonDiagonalQubits(*sub)) out.push_back(q);
+            }
+            return out;
+        }
+        switch (op.getType()) {
+            case qc::I: case qc::Z: case qc::S: case qc::Sdag: case qc::T: case qc::Tdag: case qc::Phase: case qc::RZ:
+            case qc::RZZ: case qc::GPhase: case qc::Barrier:
+                return out;
+            default:
+                break;
+        }
+        for (const auto t : op.getTargets()) out.push_back(static_cast<int>(t));
+        return out;
+    }
     static bool isMeasure(const qc::Operation& op) { return op.getType() == qc::Measure; }
     static bool isBarrier(const qc::Operation& op) { return op.getType() == qc::Barrier; }
     static bool isReset(const qc::Operation& op) { return op.getType() == qc::Reset; }

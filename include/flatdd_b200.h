@@ -98,11 +98,29 @@ int fdd_synchronize(fdd_ctx* ctx);
 /* Tunables for experiments ("dmavm_variant", "warps_per_cta", "ctas_per_sm", "prefetch", "exact_convert"). */
 int fdd_set_option(fdd_ctx* ctx, const char* key, long value);
 
-/* ---- multi-GPU wiring (one process per GPU) ---------------------------------------------
+/* ---- multi-GPU (one process per GPU) ----------------------------------
+ * The reference has no distributed code; the partition is its thread partition
+ * (seg_size = nDim / n_thread, include/dd/SwitchPackage.hpp:2146) lifted to devices.
  * fdd_comm_unique_id fills a 128-byte NCCL unique id on rank 0; the host broadcasts it
- * (torch.distributed / MPI / a file) and every rank calls fdd_comm_init with it. */
+ * (torch.distributed / MPI / a file) and every rank calls fdd_comm_init with it.  fdd_comm_init
+ * also maps the state buffers of all peers through CUDA IPC (NVLink peer access).
+ *
+ * Gates are applied shard-locally: a gate may be non-diagonal only on LOCAL physical qubits
+ * (controls and diagonal gates on global qubits are fine).  When a gate needs a global qubit the
+ * host first calls fdd_exchange_qubits(global physical bit, local physical bit) on every rank:
+ * SWAP of the two index bits = each rank trades half of its shard (8 * 2^n / G bytes each way)
+ * with the rank that differs in that global bit.  method 0: one kernel that reads the partner's
+ * half straight over NVLink peer memory; method 1: NCCL send/recv.  The host tracks the
+ * logical->physical qubit map (the reference's qc::Permutation, include/Permutation.hpp:9-25)
+ * and builds later gate DDs in physical order (dd::getDD(op, dd, permutation),
+ * include/dd/Operations.hpp:591-678); the context mirrors that map for fdd_get_permutation. */
 int fdd_comm_unique_id(void* id128);
 int fdd_comm_init(fdd_ctx* ctx, const void* id128);
+int fdd_exchange_qubits(fdd_ctx* ctx, int global_physical_bit, int local_physical_bit, int method);
+/* Bookkeeping only: the logical qubits sitting at two physical bits trade names (an uncontrolled
+ * SWAP gate absorbed into the layout, include/dd/Operations.hpp:611-620).  No data moves. */
+int fdd_relabel_qubits(fdd_ctx* ctx, int physical_bit_a, int physical_bit_b);
+int fdd_barrier(fdd_ctx* ctx);
 
 /* ---- DD -> array conversion -------------------------------------------------------------
  * Replaces SwitchSimulator::getVectorFromDDSwitch1 (include/SwitchSimulator.hpp:169-352) and

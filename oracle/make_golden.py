@@ -3,6 +3,7 @@
     python oracle/make_golden.py small     # tests/golden/<case>/   (committed)
     python oracle/make_golden.py medium    # oracle/_ref/golden/<case>/ (git-ignored, travels with gpurun)
     python oracle/make_golden.py large     # samples only, minutes to tens of minutes of CPU
+    python oracle/make_golden.py sharded   # tests/golden_sharded/<case>/: boundary traces scheduled for 2/4/8 shards
     python oracle/make_golden.py traces    # boundary traces of the bench circuits (no reference run)
     python oracle/make_golden.py samples   # truncated circuits for the bounded CPU-baseline runs
     python oracle/make_golden.py circuits  # copy the reference's 12 circuits next to the binaries (git-ignored)
@@ -53,6 +54,16 @@ LARGE = {
     "dnn_n25_f1": (REF / "circuits/dnn_n25.qasm", 8, 1, ["--no-kat"]),
     "supremacy_n26_f1": (REF / "circuits/supremacy_n26.qasm", 8, 1, ["--no-kat"]),
 }
+# sharded schedules of small circuits (trace + manifest only, committed): name -> (circuit, threads, fuse, world)
+SHARDED = {
+    "mix_n10_f1_w2": ("tests/circuits/mix_n10.qasm", 4, 1, 2),
+    "mix_n10_f0_w2": ("tests/circuits/mix_n10.qasm", 4, 0, 2),
+    "mix_n10_f3_w4": ("tests/circuits/mix_n10.qasm", 4, 3, 4),
+    "qft_n8_f0_w2": ("tests/circuits/qft_n8.qasm", 4, 0, 2),
+    "mix_n12_f1_w4": ("tests/circuits/mix_n12.qasm", 8, 1, 4),
+    "mix_n12_f3_w8": ("tests/circuits/mix_n12.qasm", 8, 3, 8),
+    "brick_n11_f3_w2": ("tests/circuits/brick_n11.qasm", 8, 3, 2),
+}
 # traces only (host DD phase + fusion schedule, no reference array phase): name -> (circuit, fuse)
 TRACES = {
     "supremacy_n26_gpu": (REF / "circuits/supremacy_n26.qasm", 3),
@@ -94,6 +105,10 @@ def main(argv):
         for name, (c, f) in TRACES.items():
             if not only or name in only:
                 run_case(ROOT / "oracle" / "_ref" / "traces", name, c, 8, 1, ["--trace-fuse", str(f), "--no-ref"])
+    elif what == "sharded":
+        for name, (c, t, f, w) in SHARDED.items():
+            if not only or name in only:
+                run_case(ROOT / "tests" / "golden_sharded", name, c, t, 1, ["--trace-fuse", str(f), "--world", str(w), "--no-ref"])
     elif what == "samples":
         make_sample("supremacy_n26", after_switch=160)
     elif what == "circuits":

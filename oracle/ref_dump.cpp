@@ -35,6 +35,7 @@ struct Args {
     int samples = 4096, katGates = 4;
     uint64_t seed = 20241017ULL;
     int traceFuse = -1; // fuse mode for the product trace (default: same as --fuse)
+    int world = 1;      // shard count the product trace is scheduled for (adds exchange records)
 };
 
 [[noreturn]] void usage() {
@@ -64,6 +65,7 @@ Args parse(int argc, char** argv) {
         else if (k == "--samples") a.samples = std::stoi(val());
         else if (k == "--kat-gates") a.katGates = std::stoi(val());
         else if (k == "--seed") a.seed = std::stoull(val());
+        else if (k == "--world") a.world = std::stoi(val());
         else usage();
     }
     if (a.file.empty() || a.out.empty()) usage();
@@ -121,7 +123,9 @@ int main(int argc, char** argv) {
         auto qcp = std::make_unique<qc::QuantumComputation>(a.file);
         nQubits = qcp->getNqubits();
         fddb200::TraceRecorder rec(a.out + "/trace.bin", static_cast<int>(nQubits));
+        if (a.world > 1) rec.setWorldSize(a.world);
         fddb200::RefGpuSwitchSimulator sim(std::move(qcp), &rec);
+        sim.worldSize = a.world;
         sim.threshold = a.thresh;
         sim.n_thread_exp = nThreadExp;
         sim.fuse = static_cast<unsigned>(a.traceFuse);
@@ -137,6 +141,7 @@ int main(int argc, char** argv) {
         man << "  \"trace\": {\"records\": " << rec.records() << ", \"switched\": " << (sim.switched ? "true" : "false")
             << ", \"switched_at_op\": " << sim.switchedAtOp << ", \"unitary_ops\": " << sim.unitaryOps
             << ", \"array_phase_ops\": " << sim.arrayPhaseOps << ", \"launches\": " << sim.launches
+            << ", \"world\": " << a.world << ", \"exchanges\": " << sim.exchanges
             << ", \"gate_merging_s\": " << sim.gateMergingTime << "},\n";
     }
     const std::size_t dim = std::size_t{1} << nQubits;
