@@ -210,42 +210,74 @@ def gpu_arm(args) -> int:
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: flatdd_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=device)
 
     lib = load_library()
-    n, records = read_trace(find_trace(f"{WORKLOAD}_gpu"))
+    workload = args.workload
+    if workload.startswith("supremacy"):  # fused with the GPU cost model
+        trace_name = f"{workload}_gpu" if world == 1 else f"{workload}_gpu_w{world}"
+    else:  # e.g. knn_n31_f0: per-gate traces exist for every shard count, also _w1
+        trace_name = f"{workload}_w{world}"
+    n, records = read_trace(find_trace(trace_name))
     assert records[0].kind == 1
     vec = records[0].dd
-    gates = [r.dd for r in records[1:]]
-    array_ops = sum(r.n_original_gates for r in records[1:])
-    dim = 1 << n
+    array_ops = sum(r.n_original_gates for r in records if r.kind == 2)
+    n_local = n - (world.bit_length() - 1)
+    local_dim = 1 << n_local
 
-    # N > 1: every rank simulates an independent replica of the circuit (weak scaling over
-    # independent circuits) until the sharded exchange path lands; see DESIGN.md section (e).
-    ctx = Context(n, device=local_rank, library=lib)
-    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
-    compiled = [ctx.compile(g) for g in gates]
+    # N > 1: the state is sharded by its top log2(N) qubits (strong scaling: the same circuit);
+    # the trace was scheduled for N shards and carries the half-shard exchanges.
+    ctx = Context(n, device=local_rank, rank=rank, world_size=world, library=lib)
+    if world > 1:
+        uid = [lib.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0, device=device)
+        ctx.comm_init(uid[0])
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
+    steps = []  # ("g", compiled) | ("x", global bit, local bit) | ("r", a, b)
+    for r in records[1:]:
+        if r.kind == 2:
+            steps.append(("g", ctx.compile(r.dd)))
+        elif r.kind == 3:
+            steps.append(("x",) + tuple(r.exchange))
+        elif r.kind == 4:
+            steps.append(("r",) + tuple(r.exchange))
+    n_gates = sum(1 for s in steps if s[0] == "g")
+    n_exch = sum(1 for s in steps if s[0] == "x")
+    method = args.exchange_method
 
     def barrier():
         ctx.synchronize()
         torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
+            dist.barrier(device_ids=[local_rank])
             torch.cuda.synchronize()
 
-    def step_resident():
+    def step_resident(exchange_events=None):
         ctx.convert(vec)
-        for g in compiled:
-            ctx.apply_compiled(g)
+        for s in steps:
+            if s[0] == "g":
+                ctx.apply_compiled(s[1])
+            elif s[0] == "x":
+                if exchange_events is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    ctx.exchange_qubits(s[1], s[2], method)
+                    e1.record(stream)
+                    exchange_events.append((e0, e1))
+                else:
+                    ctx.exchange_qubits(s[1], s[2], method)
+            else:
+                ctx.relabel_qubits(s[1], s[2])
 
-    for _ in range(max(3, args.warmup)):
+    warmup = max(3, args.warmup)
+    for _ in range(warmup):
         step_resident()
     barrier()
 
@@ -253,33 +285,56 @@ def gpu_arm(args) -> int:
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps)]
+    exchange_events = []
     launches0 = ctx.launch_count()
     barrier()
     for s in range(args.steps):
         ev[3 * s].record(stream)
         ctx.convert(vec)
         ev[3 * s + 1].record(stream)
-        for g in compiled:
-            ctx.apply_compiled(g)
+        for st in steps:
+            if st[0] == "g":
+                ctx.apply_compiled(st[1])
+            elif st[0] == "x":
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                ctx.exchange_qubits(st[1], st[2], method)
+                e1.record(stream)
+                exchange_events.append((e0, e1))
+            else:
+                ctx.relabel_qubits(st[1], st[2])
         ev[3 * s + 2].record(stream)
     barrier()
     launches = ctx.launch_count() - launches0
     total_ms = ev[0].elapsed_time(ev[3 * args.steps - 1])
     convert_ms = [ev[3 * s].elapsed_time(ev[3 * s + 1]) for s in range(args.steps)]
-    gates_ms = [ev[3 * s + 1].elapsed_time(ev[3 * s + 2]) for s in range(args.steps)]
+    body_ms = [ev[3 * s + 1].elapsed_time(ev[3 * s + 2]) for s in range(args.steps)]
+    exch_ms = [a.elapsed_time(b) for a, b in exchange_events]
     norm2 = ctx.norm2()
 
     # ---- e2e: host buffers through the C-ABI, H2D of every table and D2H of the state ------------
-    host_re = torch.empty(dim, dtype=torch.float64).pin_memory()
-    host_im = torch.empty(dim, dtype=torch.float64).pin_memory()
+    gates = [r.dd for r in records if r.kind == 2]
     h2d = table_bytes(vec) + sum(table_bytes(g) for g in gates)
-    d2h = 16 * dim
+    download = local_dim if n_local <= 28 else 1 << 20  # very large shards: a 16 MiB sample of the state
+    host_re = torch.empty(local_dim if download == local_dim else download, dtype=torch.float64).pin_memory()
+    host_im = torch.empty_like(host_re).pin_memory()
+    d2h = 16 * download
 
     def step_e2e():
         ctx.convert(vec)
-        for g in gates:
-            ctx.apply(g)
-        ctx.get_state_raw(host_re.data_ptr(), host_im.data_ptr())
+        for r in records[1:]:
+            if r.kind == 2:
+                ctx.apply(r.dd)
+            elif r.kind == 3:
+                ctx.exchange_qubits(r.exchange[0], r.exchange[1], method)
+            else:
+                ctx.relabel_qubits(*r.exchange)
+        if download == local_dim:
+            ctx.get_state_raw(host_re.data_ptr(), host_im.data_ptr())
+        else:
+            amps = ctx.get_amplitudes(0, download)
+            host_re.copy_(torch.from_numpy(np.ascontiguousarray(amps.real)))
+            host_im.copy_(torch.from_numpy(np.ascontiguousarray(amps.imag)))
 
     step_e2e()
     barrier()
@@ -292,12 +347,18 @@ def gpu_arm(args) -> int:
     clocks = sampler.stop()
     host_norm2 = float(torch.dot(host_re, host_re) + torch.dot(host_im, host_im))
 
-    # ---- max over ranks ------------------------------------------------------------------------------
+    # ---- max over ranks / sums ---------------------------------------------------------------------
     t_step_ms = total_ms / args.steps
+    exch_mean_ms = statistics.mean(exch_ms) if exch_ms else 0.0
     if world > 1:
-        t = torch.tensor([t_step_ms, e2e_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([t_step_ms, e2e_s, exch_mean_ms, statistics.mean(body_ms)], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_step_ms, e2e_s = float(t[0]), float(t[1])
+        t_step_ms, e2e_s, exch_mean_ms, body_mean = (float(x) for x in t)
+        nt = torch.tensor([norm2, host_norm2], dtype=torch.float64, device=device)
+        dist.all_reduce(nt, op=dist.ReduceOp.SUM)
+        norm2, host_norm2 = float(nt[0]), float(nt[1])
+    else:
+        body_mean = statistics.mean(body_ms)
 
     if rank == 0:
         peaks = {}
@@ -306,33 +367,42 @@ def gpu_arm(args) -> int:
             peaks = json.loads(peaks_file.read_text())
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        launch_ms = statistics.mean(gates_ms) / len(compiled)
-        achieved = 32.0 * dim / (launch_ms * 1e-3) / 1e9
+        # DMAVM launch time: the step body minus the exchanges
+        launch_ms = (body_mean - exch_mean_ms * n_exch) / max(1, n_gates)
+        achieved = 32.0 * local_dim / (launch_ms * 1e-3) / 1e9
         traffic = None
         tf = ROOT / "profiles" / "dmavm_traffic.json"
-        if tf.exists():
+        if tf.exists() and n_local == 26:
             traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
         line = {
-            "metric": METRIC, "value": world * array_ops / (t_step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": t_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD} array phase: DD->array conversion + {len(compiled)} fused DMAVM launches "
-                                   f"({array_ops} circuit ops after the switch at op 911)",
-                       "n_qubits": n, "state_bytes": 16 * dim, "fusion": "GPU-cost greedy (fuse 3)",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas",
-                       "l2": "state (1 GiB) and its ping-pong partner exceed the 126 MB L2; no flush needed"},
+            "metric": METRIC, "value": array_ops / (t_step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": t_step_ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{workload} array phase: DD->array conversion + {n_gates} fused DMAVM launches "
+                                   f"({array_ops} circuit ops after the switch)" + (f" + {n_exch} half-shard exchanges" if world > 1 else ""),
+                       "n_qubits": n, "state_bytes": 16 << n, "fusion": "GPU-cost greedy (fuse 3)" if workload.startswith("supremacy") else "per gate (fuse 0)",
+                       "parallelism": "1 GPU" if world == 1 else f"state sharded over {world} GPUs by its top {world.bit_length() - 1} qubits; "
+                                      f"qubit remap + half-shard exchange ({'peer-memory kernel' if method == 0 else 'NCCL send/recv'})",
+                       "l2": f"shard ({(16 << n_local) >> 20} MiB) and its ping-pong partner exceed the 126 MB L2; no flush needed"
+                             if n_local >= 24 else "shard fits L2 at this GPU count (strong scaling of a 1 GiB state)"},
             "seconds_per_circuit": t_step_ms * 1e-3,
             "convert_ms": statistics.mean(convert_ms), "dmavm_ms_per_launch": launch_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "dmavm_tile_kernel", "peak_source": peak_src, "bytes_per_launch": 32 * dim,
-                         "convert_gbs": 16.0 * dim / (statistics.mean(convert_ms) * 1e-3) / 1e9},
-            "e2e": {"value": world * array_ops / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                         "kernel": "dmavm_tile_kernel", "peak_source": peak_src, "bytes_per_launch": 32 * local_dim,
+                         "convert_gbs": 16.0 * local_dim / (statistics.mean(convert_ms) * 1e-3) / 1e9},
+            "e2e": {"value": array_ops / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "seconds_per_circuit": e2e_s, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "check": {"norm2_device": norm2, "norm2_host_copy": host_norm2},
         }
-        if world == 1 and not args.no_cpu:
+        if world > 1 and n_exch:
+            half_bytes = 8.0 * local_dim
+            gbs = half_bytes / (exch_mean_ms * 1e-3) / 1e9
+            line["exchange"] = {"per_step": n_exch, "bytes_each_way_per_gpu": half_bytes, "ms_mean": exch_mean_ms, "gbs_per_direction": gbs,
+                                "frac_of_nvlink_nominal_900": gbs / 900.0, "frac_of_nvlink_measured_770": gbs / 770.0,
+                                "method": "peer-memory kernel (barrier + kernel + barrier)" if method == 0 else "NCCL send/recv + D2D copy"}
+        if world == 1 and not args.no_cpu and workload == WORKLOAD:
             try:
                 r = run_reference_once(host_threads())
                 secs = r["array_s"] + r["convert_s"]
@@ -357,6 +427,8 @@ def main() -> int:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="flatdd_b200", choices=["flatdd_b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default=WORKLOAD, help="supremacy_n26 (default), supremacy_n20, knn_n31_f0, ... (needs its boundary trace)")
+    ap.add_argument("--exchange-method", type=int, default=0, help="0 = peer-memory kernel, 1 = NCCL send/recv")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

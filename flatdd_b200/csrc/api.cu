@@ -100,6 +100,8 @@ struct fdd_ctx {
     int ctasPerSm = 0; // 0 = as many as shared memory allows (capped)
     int prefetch = 8;
     int forceMode = -1;   // experiments: force the tile-kernel MODE (1, 2 or 3) where it applies
+    int exchangeUnroll = 8;
+    int exchangeCtasPerSm = 4;
     // scratch
     double* dPartial = nullptr;
     double* dNorm = nullptr;
@@ -437,6 +439,8 @@ int fdd_set_option(fdd_ctx* ctx, const char* key, long value) {
         else if (k == "ctas_per_sm") ctx->ctasPerSm = static_cast<int>(value);
         else if (k == "prefetch") ctx->prefetch = static_cast<int>(value);
         else if (k == "tile_mode") ctx->forceMode = static_cast<int>(value);
+        else if (k == "exchange_unroll") ctx->exchangeUnroll = static_cast<int>(value);
+        else if (k == "exchange_ctas_per_sm") ctx->exchangeCtasPerSm = static_cast<int>(value);
         else throw std::invalid_argument("unknown option " + k);
     });
 }
@@ -523,8 +527,14 @@ void exchangeBits(fdd_ctx* c, int pg, int pl, int method) {
     const uint64_t dim = c->localDim();
     if (method == 0) {
         streamBarrier(c); // every rank has finished writing its current buffer
-        const int grid = c->smCount * 8;
-        exchange_p2p_kernel<<<grid, 256, 0, c->stream>>>(c->buf[c->cur], c->peerBuf[c->cur][partner], c->buf[c->cur ^ 1], dim, pl, myBit);
+        const int grid = c->smCount * (c->exchangeCtasPerSm > 0 ? c->exchangeCtasPerSm : 4);
+        if (c->exchangeUnroll == 4) {
+            exchange_p2p_kernel<4><<<grid, 256, 0, c->stream>>>(c->buf[c->cur], c->peerBuf[c->cur][partner], c->buf[c->cur ^ 1], dim, pl, myBit);
+        } else if (c->exchangeUnroll == 16) {
+            exchange_p2p_kernel<16><<<grid, 256, 0, c->stream>>>(c->buf[c->cur], c->peerBuf[c->cur][partner], c->buf[c->cur ^ 1], dim, pl, myBit);
+        } else {
+            exchange_p2p_kernel<8><<<grid, 256, 0, c->stream>>>(c->buf[c->cur], c->peerBuf[c->cur][partner], c->buf[c->cur ^ 1], dim, pl, myBit);
+        }
         CUDA_TRY(cudaGetLastError());
         c->launches++;
         streamBarrier(c); // nobody overwrites a buffer a peer may still be reading

@@ -6,6 +6,8 @@
 //     reads the partner's half shard straight over NVLink (NVSwitch: full bandwidth to any peer).
 #pragma once
 
+#include "kernels.cuh"
+
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -66,25 +68,37 @@ private:
 // value `myBit`: the half with bit pl == myBit stays, the other half is replaced by the
 // partner's half with bit pl == myBit.  Out of place (mine -> out) so that the partner can read
 // `mine` at the same time; half of the reads cross NVLink, 16-byte vectors, 4 in flight per thread.
+template <int U>
 __global__ void __launch_bounds__(256) exchange_p2p_kernel(const double2* __restrict__ mine, const double2* __restrict__ partner,
                                                            double2* __restrict__ out, uint64_t n, int pl, int myBit) {
+    // h enumerates the half space (index without bit pl); every h yields one kept and one traded amplitude
+    const uint64_t half = n >> 1;
+    const uint64_t lowMask = (uint64_t{1} << pl) - 1;
+    const uint64_t keepBit = static_cast<uint64_t>(myBit) << pl;
     const uint64_t flip = uint64_t{1} << pl;
     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
-    uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < n; i += 4 * stride) {
-        double2 v[4];
+    uint64_t h = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (; h + (U - 1) * stride < half; h += U * stride) {
+        double2 far[U], near[U];
+        uint64_t at[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint64_t j = i + u * stride;
-            const bool keep = static_cast<int>((j >> pl) & 1ULL) == myBit;
-            v[u] = keep ? mine[j] : partner[j ^ flip];
+        for (int u = 0; u < U; ++u) {
+            const uint64_t x = h + u * stride;
+            at[u] = ((x & ~lowMask) << 1) | (x & lowMask) | keepBit; // index with bit pl == myBit
+            far[u] = ld_stream(partner + at[u]);                    // crosses NVLink
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) out[i + u * stride] = v[u];
+        for (int u = 0; u < U; ++u) near[u] = ld_stream(mine + at[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            st_stream(out + at[u], near[u]);
+            st_stream(out + (at[u] ^ flip), far[u]);
+        }
     }
-    for (; i < n; i += stride) {
-        const bool keep = static_cast<int>((i >> pl) & 1ULL) == myBit;
-        out[i] = keep ? mine[i] : partner[i ^ flip];
+    for (; h < half; h += stride) {
+        const uint64_t i = ((h & ~lowMask) << 1) | (h & lowMask) | keepBit;
+        out[i] = mine[i];
+        out[i ^ flip] = partner[i];
     }
 }
 

@@ -67,6 +67,15 @@ SHARDED = {
 # traces only (host DD phase + fusion schedule, no reference array phase): name -> (circuit, fuse)
 TRACES = {
     "supremacy_n26_gpu": (REF / "circuits/supremacy_n26.qasm", 3),
+    "supremacy_n26_gpu_w2": (REF / "circuits/supremacy_n26.qasm", 3, 2),
+    "supremacy_n26_gpu_w4": (REF / "circuits/supremacy_n26.qasm", 3, 4),
+    "supremacy_n26_gpu_w8": (REF / "circuits/supremacy_n26.qasm", 3, 8),
+    "supremacy_n20_gpu_w2": (REF / "circuits/supremacy_n20.qasm", 3, 2),
+    "knn_n25_f0_w2": (REF / "circuits/knn_n25.qasm", 0, 2),
+    "knn_n31_f0_w1": (REF / "circuits/knn_n31.qasm", 0, 1),
+    "knn_n31_f0_w2": (REF / "circuits/knn_n31.qasm", 0, 2),
+    "knn_n31_f0_w4": (REF / "circuits/knn_n31.qasm", 0, 4),
+    "knn_n31_f0_w8": (REF / "circuits/knn_n31.qasm", 0, 8),
     "supremacy_n26_ref": (REF / "circuits/supremacy_n26.qasm", 1),
     "supremacy_n24_gpu": (REF / "circuits/supremacy_n24.qasm", 3),
     "supremacy_n20_gpu": (REF / "circuits/supremacy_n20.qasm", 3),
@@ -102,9 +111,10 @@ def main(argv):
             if not only or name in only:
                 run_case(ROOT / "oracle" / "_ref" / "golden", name, c, t, f, extra)
     elif what == "traces":
-        for name, (c, f) in TRACES.items():
+        for name, spec in TRACES.items():
             if not only or name in only:
-                run_case(ROOT / "oracle" / "_ref" / "traces", name, c, 8, 1, ["--trace-fuse", str(f), "--no-ref"])
+                extra = ["--trace-fuse", str(spec[1]), "--no-ref"] + (["--world", str(spec[2])] if len(spec) > 2 else [])
+                run_case(ROOT / "oracle" / "_ref" / "traces", name, spec[0], 8, 1, extra)
     elif what == "sharded":
         for name, (c, t, f, w) in SHARDED.items():
             if not only or name in only:

@@ -1,0 +1,103 @@
+"""Multi-GPU parity (needs >= 2 GPUs; `gpurun --gpus 2` or more).  One process per GPU: sharded
+contexts over the C-ABI, NCCL unique id broadcast over gloo, boundary traces scheduled for the
+shard count, both exchange methods (0 = peer-memory kernel, 1 = NCCL send/recv), results
+gathered and compared with the reference's final state."""
+import json
+import os
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from flatdd_b200 import read_trace
+from flatdd_b200.sharded import GpuShard, replay, to_logical_order
+from tests import golden_util as G
+from tests.test_sharded_cpu import CASES, SHARDED, reference_final
+
+pytestmark = pytest.mark.gpu
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def n_gpus() -> int:
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def _worker(rank, world, trace_path, port, out_dir, method, canonicalize):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from flatdd_b200 import Context, load_library
+        lib = load_library()
+        uid = [lib.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        n, records = read_trace(trace_path)
+        with Context(n, device=rank, rank=rank, world_size=world, library=lib) as ctx:
+            ctx.comm_init(uid[0])
+            shard = GpuShard(ctx, exchange_method=method)
+            l2p = replay(records, shard, n)
+            assert list(ctx.permutation()) == l2p  # the context mirrors the layout
+            if canonicalize:
+                ctx.canonicalize()
+                assert list(ctx.permutation()) == list(range(n))
+                l2p = list(range(n))
+            re, im = ctx.get_state()
+            ctx.barrier()
+        local = torch.from_numpy(np.stack([re, im]))
+        gathered = [torch.empty_like(local) for _ in range(world)] if rank == 0 else None
+        dist.gather(local, gathered, dst=0)
+        if rank == 0:
+            full = np.concatenate([g[0].numpy() + 1j * g[1].numpy() for g in gathered])
+            np.save(Path(out_dir) / "state.npy", to_logical_order(full, l2p))
+    finally:
+        dist.destroy_process_group()
+
+
+def run_sharded(trace_path, world, tmp_path, method=0, canonicalize=False):
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, str(trace_path), port, str(tmp_path), method, canonicalize), nprocs=world, join=True)
+    return np.load(Path(tmp_path) / "state.npy")
+
+
+def _world(case):
+    return json.loads((SHARDED / case / "manifest.json").read_text())["trace"]["world"]
+
+
+@pytest.mark.parametrize("method", [0, 1])
+@pytest.mark.parametrize("case", CASES)
+def test_sharded_trace_vs_reference(case, method, tmp_path):
+    world = _world(case)
+    if n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _, want = reference_final(case)
+    got = run_sharded(SHARDED / case / "trace.bin", world, tmp_path, method=method)
+    assert np.max(np.abs(got - want)) < 1e-10
+    assert 1.0 - abs(np.vdot(got, want)) ** 2 / (np.vdot(got, got).real * np.vdot(want, want).real) < 1e-10
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c.endswith("_w2")][:2])
+def test_canonicalize_restores_logical_layout(case, tmp_path):
+    if n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    _, want = reference_final(case)
+    got = run_sharded(SHARDED / case / "trace.bin", 2, tmp_path, method=0, canonicalize=True)
+    assert np.max(np.abs(got - want)) < 1e-10
+
+
+@pytest.mark.parametrize("name,golden", [("supremacy_n20_gpu_w2", "supremacy_n20_f1"), ("knn_n25_f0_w2", "knn_n25_f1")])
+def test_sharded_reference_circuits(name, golden, tmp_path):
+    """Reference circuits sharded over 2 GPUs against golden data of the compiled reference."""
+    trace = G.TRACES / name / "trace.bin"
+    if n_gpus() < 2 or not trace.exists() or golden not in G.cases(G.TRAVEL):
+        pytest.skip("needs 2 GPUs and the travel goldens")
+    got = run_sharded(trace, 2, tmp_path)
+    if (G.TRAVEL / golden / "final_re.f64").exists():
+        fr, fi = G.final_state(golden, G.TRAVEL)
+        assert np.max(np.abs(got - (fr + 1j * fi))) < 1e-10
+    else:
+        idx, sr, si = G.samples(golden, G.TRAVEL)
+        assert np.max(np.abs(got[idx.astype(np.int64)] - (sr + 1j * si))) < 1e-10
