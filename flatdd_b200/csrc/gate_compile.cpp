@@ -397,15 +397,19 @@ CompiledGate compileGate(const fdd_matdd& g, int nLocal) {
 }
 
 double costGpuNs(const CompiledGate& c, double hbmGBs, double fp64GFlops) {
+    // One launch costs max(HBM time, fp64 time, issue time).  Measured on B200 at n = 26 (profiles/r01_*):
+    // paths*K <= 4 runs at the HBM bound (0.37 ms), paths*K = 8 at 0.63 ms.  The issue term is kept
+    // deliberately pessimistic (it prices paths*K = 8 at ~0.9 ms): the greedy pass is myopic, and an
+    // accurate price makes it spend the dense budget early — the measured circuit time was 133 ms
+    // with the accurate model against 118 ms with this one (supremacy_n26, 216 vs 265 launches).
     const double amps = std::ldexp(1.0, c.n);
     const double memNs = 32.0 * amps / hbmGBs; // GB/s == B/ns
-    // 8 flop per MAC plus one complex multiply (6 flop) to combine upper and lower weights
     const double flopNs = 14.0 * static_cast<double>(c.nnz) / fp64GFlops;
-    // issue model: warp instructions per 32-row segment, 148 SMs x 4 schedulers at ~1.8 GHz, ~60% usable
     const double instrPerSeg = 40.0 + c.maxPaths * (14.0 + 16.0 * c.kMax) + 12.0 * c.upperDepth * c.maxPaths / 4.0;
     const double issueNs = (amps / 32.0) * instrPerSeg / (148.0 * 4.0 * 1.8 * 0.6);
+    const double walkPenalty = c.tileable ? 1.0 : 3.0; // gates that do not tile take the walk kernel
     const double launchNs = 3000.0;
-    return std::max(memNs, std::max(flopNs, issueNs)) + launchNs;
+    return walkPenalty * std::max(memNs, std::max(flopNs, issueNs)) + launchNs;
 }
 
 } // namespace fddb200

@@ -40,6 +40,7 @@ SMALL = {
     "mix_n12_f1": ("tests/circuits/mix_n12.qasm", 8, 1, ["--kat-gates", "1"]),
 }
 MEDIUM = {
+    "synth_n20_f1": (ROOT / "oracle/_ref/circuits/synth_n20.qasm", 8, 1, ["--no-kat", "--full-state"]),
     "vqe_n16_f0": (REF / "circuits/vqe_n16.qasm", 8, 0, ["--kat-gates", "2", "--full-state"]),
     "vqe_n16_f1": (REF / "circuits/vqe_n16.qasm", 8, 1, ["--kat-gates", "1", "--full-state"]),
     "dnn_n16_f1": (REF / "circuits/dnn_n16.qasm", 8, 1, ["--kat-gates", "1", "--full-state"]),
@@ -48,6 +49,7 @@ MEDIUM = {
     "dnn_n20_f1": (REF / "circuits/dnn_n20.qasm", 8, 1, ["--no-kat"]),
 }
 LARGE = {
+    "adder_n28_f0": (REF / "circuits/adder_n28.qasm", 8, 0, ["--no-kat"]),
     "knn_n25_f1": (REF / "circuits/knn_n25.qasm", 8, 1, ["--no-kat"]),
     "swap_test_n25_f1": (REF / "circuits/swap_test_n25.qasm", 8, 1, ["--no-kat"]),
     "supremacy_n24_f1": (REF / "circuits/supremacy_n24.qasm", 8, 1, ["--no-kat"]),
@@ -72,6 +74,14 @@ TRACES = {
     "supremacy_n26_gpu_w8": (REF / "circuits/supremacy_n26.qasm", 3, 8),
     "supremacy_n20_gpu_w2": (REF / "circuits/supremacy_n20.qasm", 3, 2),
     "knn_n25_f0_w2": (REF / "circuits/knn_n25.qasm", 0, 2),
+    "synth_n26_w1": (ROOT / "oracle/_ref/circuits/synth_n26.qasm", 3, 1),
+    "synth_n26_w8": (ROOT / "oracle/_ref/circuits/synth_n26.qasm", 3, 8),
+    "synth_n30_w1": (ROOT / "oracle/_ref/circuits/synth_n30.qasm", 3, 1),
+    "synth_n30_w2": (ROOT / "oracle/_ref/circuits/synth_n30.qasm", 3, 2),
+    "synth_n30_w4": (ROOT / "oracle/_ref/circuits/synth_n30.qasm", 3, 4),
+    "synth_n30_w8": (ROOT / "oracle/_ref/circuits/synth_n30.qasm", 3, 8),
+    "synth_n34_w8": (ROOT / "oracle/_ref/circuits/synth_n34.qasm", 3, 8),
+    "synth_n20_w2": (ROOT / "oracle/_ref/circuits/synth_n20.qasm", 3, 2),
     "knn_n31_f0_w1": (REF / "circuits/knn_n31.qasm", 0, 1),
     "knn_n31_f0_w2": (REF / "circuits/knn_n31.qasm", 0, 2),
     "knn_n31_f0_w4": (REF / "circuits/knn_n31.qasm", 0, 4),
