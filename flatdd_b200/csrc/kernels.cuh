@@ -20,6 +20,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace fddb200 {
 
 constexpr int kWarp = 32;
@@ -492,7 +494,6 @@ __device__ __forceinline__ uint32_t depositAround(uint32_t x, uint32_t mask) {
 template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dmavm_tile_kernel(const WalkParams p) {
     constexpr int T = TileShape<TB>::T;
     constexpr int R = TileShape<TB>::R;
-    constexpr int JC = TileShape<TB>::JC;
     extern __shared__ __align__(16) unsigned char smemRaw[];
     unsigned char* cursor = smemRaw;
     const UpperNode* upper = p.upper;
@@ -609,8 +610,16 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
                     while (code >= 0) {
                         const UpperNode& nd = upper[code];
                         const int sb = nd.slotBit;
-                        const int rb = sb >= 0 ? ((tl >> sb) & 1) : static_cast<int>((rowSeg >> (nd.level - S)) & 1u);
-                        const uint32_t bit = sb >= 0 ? (1u << sb) : 0u;
+                        if (sb < 0) {
+                            // a level outside the tile bits is diagonal by construction: one successor, no column change
+                            const int d = 3 * static_cast<int>((rowSeg >> (nd.level - S)) & 1u);
+                            const int next = nd.child[d];
+                            if (next != FDD_TERMINAL) w = cmul(w, reinterpret_cast<const double2*>(nd.w)[d]);
+                            code = next;
+                            continue;
+                        }
+                        const int rb = (tl >> sb) & 1;
+                        const uint32_t bit = 1u << sb;
                         const int2 ch = *reinterpret_cast<const int2*>(&nd.child[2 * rb]);
                         const double2* nw = reinterpret_cast<const double2*>(nd.w) + 2 * rb;
                         if (ch.x != FDD_TERMINAL) {
@@ -654,80 +663,100 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
         __syncwarp();
 
         // =================== phase B: stream the sub-tiles, lane = amplitude ========================
-        for (int q = 0; q < Q; ++q) {
-            cp_async_wait<R - 1>(); // groups complete in order: the oldest one is this sub-tile
+        // G consecutive sub-tiles are computed together so that at least four output segments
+        // (independent FMA chains) are in flight even when a sub-tile is one or two segments
+        auto computeGroup = [&](auto groupTag, int q) {
+            constexpr int G = decltype(groupTag)::value;
+            constexpr int NACC = (G * T < 8) ? G * T : 8; // accumulators per pass
+            cp_async_wait<R - G>(); // groups complete in order: the G oldest ones are these sub-tiles
             __syncwarp();
-            const double2* stage = ring + useSlot * T * 32;
 #pragma unroll
-            for (int j0 = 0; j0 < T; j0 += JC) {
-                double2 acc[JC];
+            for (int j0 = 0; j0 < G * T; j0 += NACC) {
+                double2 acc[NACC];
 #pragma unroll
-                for (int jj = 0; jj < JC; ++jj) acc[jj] = make_double2(0.0, 0.0);
-                const int rowBase = (q << TB) + j0; // lane that owns output segment jj = 0
+                for (int a = 0; a < NACC; ++a) acc[a] = make_double2(0.0, 0.0);
+                // accumulator a <-> output segment (q + (j0+a)/T, slot (j0+a)%T): lane rowBase+a of phase A
+                const int rowBase = (q << TB) + j0;
+                auto stageOf = [&](int a) -> const double2* {
+                    const int g = (j0 + a) / T; // compile-time after unrolling
+                    int slot = useSlot + g;
+                    if (slot >= R) slot -= R;
+                    return ring + slot * T * 32;
+                };
                 if (MODE == 0 || MODE == 2) {
                     for (int i = 0; i < P; ++i) {
 #pragma unroll
-                        for (int jj = 0; jj < JC; ++jj) {
-                            const double2 w = eW[i * 32 + rowBase + jj];
-                            const uint32_t pk = ePack[i * 32 + rowBase + jj];
-                            cmac(acc[jj], w, stage[(pk & 31u) * 32 + lane]);
+                        for (int a = 0; a < NACC; ++a) {
+                            const double2 w = eW[i * 32 + rowBase + a];
+                            const uint32_t pk = ePack[i * 32 + rowBase + a];
+                            cmac(acc[a], w, stageOf(a)[(pk & 31u) * 32 + lane]);
                         }
                     }
                     if (MODE == 2) {
-                        double2 out[JC];
+                        double2 out[NACC];
 #pragma unroll
-                        for (int jj = 0; jj < JC; ++jj) out[jj] = make_double2(0.0, 0.0);
+                        for (int a = 0; a < NACC; ++a) out[a] = make_double2(0.0, 0.0);
 #pragma unroll
                         for (int k = 0; k < KR; ++k) {
 #pragma unroll
-                            for (int jj = 0; jj < JC; ++jj) cmac(out[jj], Lw[k], shfl2(acc[jj], Lc[k]));
+                            for (int a = 0; a < NACC; ++a) cmac(out[a], Lw[k], shfl2(acc[a], Lc[k]));
                         }
 #pragma unroll
-                        for (int jj = 0; jj < JC; ++jj) acc[jj] = out[jj];
+                        for (int a = 0; a < NACC; ++a) acc[a] = out[a];
                     }
                 } else if (MODE == 1) {
                     for (int i = 0; i < P; ++i) {
 #pragma unroll
-                        for (int jj = 0; jj < JC; ++jj) {
-                            const double2 w = eW[i * 32 + rowBase + jj];
-                            const uint32_t pk = ePack[i * 32 + rowBase + jj];
-                            const double2* src = stage + (pk & 31u) * 32;
+                        for (int a = 0; a < NACC; ++a) {
+                            const double2 w = eW[i * 32 + rowBase + a];
+                            const uint32_t pk = ePack[i * 32 + rowBase + a];
+                            const double2* src = stageOf(a) + (pk & 31u) * 32;
                             double2 t = make_double2(0.0, 0.0);
 #pragma unroll
                             for (int k = 0; k < KR; ++k) cmac(t, Lw[k], src[Lc[k]]);
-                            cmac(acc[jj], w, t);
+                            cmac(acc[a], w, t);
                         }
                     }
                 } else {
                     for (int i = 0; i < P; ++i) {
 #pragma unroll
-                        for (int jj = 0; jj < JC; ++jj) {
-                            const double2 w = eW[i * 32 + rowBase + jj];
-                            const uint32_t pk = ePack[i * 32 + rowBase + jj];
-                            const double2* src = stage + (pk & 31u) * 32;
-                            const int at0 = static_cast<int>(pk >> 8) * p.kMax * 32 + lane;
+                        for (int a = 0; a < NACC; ++a) {
+                            const double2 w = eW[i * 32 + rowBase + a];
+                            const uint32_t pk = ePack[i * 32 + rowBase + a];
+                            const double2* src = stageOf(a) + (pk & 31u) * 32;
+                            // KT > 0: the host padded every sub table to exactly KT entries per row
+                            const int at0 = static_cast<int>(pk >> 8) * (KT > 0 ? KT : p.kMax) * 32 + lane;
                             double2 t = make_double2(0.0, 0.0);
                             if (KT > 0) {
+                                int col[KT > 0 ? KT : 1];
 #pragma unroll
-                                for (int k = 0; k < (KT > 0 ? KT : 1); ++k) {
-                                    if (k < p.kMax) cmac(t, subW[at0 + k * 32], src[subCol[at0 + k * 32]]);
-                                }
+                                for (int k = 0; k < (KT > 0 ? KT : 1); ++k) col[k] = subCol[at0 + k * 32];
+#pragma unroll
+                                for (int k = 0; k < (KT > 0 ? KT : 1); ++k) cmac(t, subW[at0 + k * 32], src[col[k]]);
                             } else {
                                 for (int k = 0; k < p.kMax; ++k) cmac(t, subW[at0 + k * 32], src[subCol[at0 + k * 32]]);
                             }
-                            cmac(acc[jj], w, t);
+                            cmac(acc[a], w, t);
                         }
                     }
                 }
 #pragma unroll
-                for (int jj = 0; jj < JC; ++jj) {
-                    const uint32_t dep = __shfl_sync(0xffffffffu, myDep, rowBase + jj);
-                    if (lane < segLen) st_stream(p.z + ((static_cast<uint64_t>(base | dep)) << S) + lane, acc[jj]);
+                for (int a = 0; a < NACC; ++a) {
+                    const uint32_t dep = __shfl_sync(0xffffffffu, myDep, rowBase + a);
+                    if (lane < segLen) st_stream(p.z + ((static_cast<uint64_t>(base | dep)) << S) + lane, acc[a]);
                 }
             }
-            __syncwarp(); // every lane is done with the stage slot before it is refilled
-            useSlot = (useSlot + 1 == R) ? 0 : useSlot + 1;
-            issueNext();
+            __syncwarp(); // every lane is done with the stage slots before they are refilled
+            useSlot += G;
+            if (useSlot >= R) useSlot -= R;
+#pragma unroll
+            for (int g = 0; g < G; ++g) issueNext();
+        };
+        constexpr int GS = (T >= 4) ? 1 : 4 / T;
+        if (GS > 1 && Q >= GS) {
+            for (int q = 0; q < Q; q += GS) computeGroup(std::integral_constant<int, GS>{}, q);
+        } else {
+            for (int q = 0; q < Q; ++q) computeGroup(std::integral_constant<int, 1>{}, q);
         }
     }
     cp_async_wait<0>();
