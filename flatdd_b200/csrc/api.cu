@@ -230,7 +230,7 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
     p.tablesInSmem = tableBytes <= kTableSmemLimit ? 1 : 0;
     const size_t fixed = p.tablesInSmem ? tableBytes : 0;
 
-    if (c->variant >= 2 && h.tileable && h.upper.size() < (1u << 22) && h.nSub < (1 << 22)) {
+    if (c->variant == 2 && h.tileable && h.upper.size() < (1u << 22) && h.nSub < (1 << 22)) {
         // ---- tile kernel ----------------------------------------------------------------------------
         bool allIdentity = true;
         for (uint8_t f : h.subFlags) allIdentity = allIdentity && (f & SUB_IDENTITY);
@@ -282,13 +282,28 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
         // the per-warp state does not fit: fall through to the walk kernel
         p.nTiles = (p.nSeg + 31) / 32;
     }
-    const int variant = c->variant == 0 ? 0 : 1;
+    const int variant = c->variant == 0 ? 0 : 1; // 9 forces the chunk kernel below
     const size_t perWarp = walkWarpSmem(p.maxPaths, p.stackCap, variant == 1 ? D : 0);
     int warps = std::max(1, std::min(c->warpsPerCta > 0 ? c->warpsPerCta : 8, 16));
     while (warps > 1 && fixed + warps * perWarp > kSmemBudget) warps >>= 1;
-    if (fixed + warps * perWarp > kSmemBudget) {
-        throw std::length_error("gate too dense for one launch: " + std::to_string(h.maxPaths) +
-                                " source segments per output segment; split the fused gate");
+    if (fixed + warps * perWarp > kSmemBudget || c->variant == 9) {
+        // too many paths per segment for a resident list: bounded lists + partial sums in shared memory
+        const size_t perWarpC = chunkWarpSmem(p.stackCap);
+        int warpsC = 4;
+        while (warpsC > 1 && warpsC * perWarpC > kSmemBudget) warpsC >>= 1;
+        if (warpsC * perWarpC > kSmemBudget) throw std::length_error("gate needs a deeper walk stack than shared memory holds");
+        const size_t smemC = warpsC * perWarpC;
+        CUDA_TRY(cudaFuncSetAttribute(dmavm_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
+        int residentC = 1;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&residentC, dmavm_chunk_kernel, warpsC * 32, smemC));
+        const uint32_t ctasC = (p.nTiles + warpsC - 1) / warpsC;
+        const int gridC = static_cast<int>(std::max<uint32_t>(1, std::min<uint32_t>(ctasC, static_cast<uint32_t>(c->smCount * std::max(1, residentC)))));
+        Timed t(c);
+        dmavm_chunk_kernel<<<gridC, warpsC * 32, smemC, c->stream>>>(p);
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+        c->cur ^= 1;
+        return;
     }
     const size_t smem = fixed + warps * perWarp;
     int perSm = static_cast<int>(kSmemBudget / std::max<size_t>(smem, 1));
@@ -772,9 +787,6 @@ int fdd_cost_gpu(const fdd_matdd* gate, double hbm_gbs, double fp64_gflops, doub
     return guarded([&] {
         if (gate == nullptr || nanoseconds == nullptr) throw std::invalid_argument("null argument");
         const CompiledGate c = compileGate(*gate);
-        const size_t perWarp = walkWarpSmem(c.maxPaths, c.stackCap, 8);
-        const size_t tables = walkTableSmem(static_cast<int>(c.upper.size()), c.nSub, c.kMax);
-        if ((tables <= kTableSmemLimit ? tables : 0) + perWarp > kSmemBudget) throw std::length_error("gate too dense for one launch");
         *nanoseconds = costGpuNs(c, hbm_gbs, fp64_gflops);
     });
 }

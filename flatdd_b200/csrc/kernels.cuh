@@ -436,6 +436,133 @@ template <int VARIANT> __global__ void __launch_bounds__(512) dmavm_walk_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
+// DMAVM chunk kernel: any gate, however dense
+// ------------------------------------------------------------------------------------------------
+// Same walk as dmavm_walk_kernel<0>, but the per-segment entry list is bounded (CAP entries): the
+// depth-first walk of every lane is suspended when its list is full, the partial lists are
+// applied and accumulated into a per-warp tile of partial sums in shared memory, and the walk
+// resumes where it stopped.  Used when the path count of a gate (for example a fused block that is
+// dense on nine upper qubits: 512 sources per segment) does not fit the other kernels.
+constexpr int kChunkCap = 8;
+__host__ __device__ inline size_t chunkWarpSmem(int stackCap) {
+    return static_cast<size_t>(kChunkCap + stackCap) * 32 * 24 + 32 * 32 * 16;
+}
+
+__global__ void __launch_bounds__(128) dmavm_chunk_kernel(const WalkParams p) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warpsPerCta = blockDim.x >> 5;
+    unsigned char* mine = smemRaw + static_cast<size_t>(warp) * chunkWarpSmem(p.stackCap);
+    const int nSlots = kChunkCap + p.stackCap;
+    double2* eW = reinterpret_cast<double2*>(mine);
+    int32_t* eCode = reinterpret_cast<int32_t*>(mine + static_cast<size_t>(nSlots) * 32 * 16);
+    uint32_t* eCol = reinterpret_cast<uint32_t*>(mine + static_cast<size_t>(nSlots) * 32 * 20);
+    double2* accTile = reinterpret_cast<double2*>(mine + static_cast<size_t>(nSlots) * 32 * 24); // [32 segments][32 lanes]
+    const int stackBase = kChunkCap;
+    const UpperNode* upper = p.upper; // tables stay in global memory (L1/L2 cached): this path is not tuned
+
+    const uint32_t warpGlobal = blockIdx.x * warpsPerCta + warp;
+    const uint32_t warpStride = gridDim.x * warpsPerCta;
+    const int S = p.segBits;
+    const int segLen = 1 << S;
+    const int upperLocalBits = p.nLocal - S;
+    const uint32_t localSegMask = (upperLocalBits >= 32) ? 0xffffffffu : ((1u << upperLocalBits) - 1u);
+
+    for (uint32_t tile = warpGlobal; tile < p.nTiles; tile += warpStride) {
+        const uint32_t seg = tile * 32u + lane;
+        const int nSegTile = static_cast<int>(min(32u, p.nSeg - tile * 32u));
+        for (int j = 0; j < 32; ++j) accTile[j * 32 + lane] = make_double2(0.0, 0.0);
+        // resumable depth-first walk state of this lane
+        const uint32_t rowSeg = (p.rank << upperLocalBits) | seg;
+        bool done = !(seg < p.nSeg && p.root != FDD_TERMINAL);
+        bool pendingPop = false;
+        int sp = 0;
+        int code = p.root;
+        double2 w = p.rootW;
+        uint32_t col = rowSeg;
+        for (;;) {
+            int cnt = 0;
+            while (!done && cnt < kChunkCap) {
+                if (pendingPop) {
+                    if (sp == 0) {
+                        done = true;
+                        break;
+                    }
+                    --sp;
+                    const int slot = (stackBase + sp) * 32 + lane;
+                    w = eW[slot];
+                    code = eCode[slot];
+                    col = eCol[slot];
+                    pendingPop = false;
+                }
+                while (code >= 0) {
+                    const UpperNode& nd = upper[code];
+                    const int sh = nd.level - S;
+                    const int rb = static_cast<int>((rowSeg >> sh) & 1u);
+                    const int2 ch = *reinterpret_cast<const int2*>(&nd.child[2 * rb]);
+                    const double2* nw = reinterpret_cast<const double2*>(nd.w) + 2 * rb;
+                    if (ch.x != FDD_TERMINAL) {
+                        if (ch.y != FDD_TERMINAL) {
+                            const int slot = (stackBase + sp) * 32 + lane;
+                            eW[slot] = cmul(w, nw[1]);
+                            eCode[slot] = ch.y;
+                            eCol[slot] = col | (1u << sh);
+                            ++sp;
+                        }
+                        w = cmul(w, nw[0]);
+                        col &= ~(1u << sh);
+                        code = ch.x;
+                    } else if (ch.y != FDD_TERMINAL) {
+                        w = cmul(w, nw[1]);
+                        col |= (1u << sh);
+                        code = ch.y;
+                    } else {
+                        code = FDD_TERMINAL;
+                    }
+                }
+                if (code <= -2) {
+                    const int slot = cnt * 32 + lane;
+                    eW[slot] = w;
+                    eCode[slot] = -2 - code;
+                    eCol[slot] = col;
+                    ++cnt;
+                }
+                pendingPop = true;
+            }
+            __syncwarp();
+            // apply the partial lists
+            for (int j = 0; j < nSegTile; ++j) {
+                const int cj = __shfl_sync(0xffffffffu, cnt, j);
+                if (cj == 0) continue;
+                double2 acc = accTile[j * 32 + lane];
+                for (int i = 0; i < cj; ++i) {
+                    const int slot = i * 32 + j;
+                    const double2 we = eW[slot];
+                    const int sub = eCode[slot];
+                    const uint32_t c = eCol[slot];
+                    const double2* src = (p.worldBits == 0) ? p.y : p.peerY[c >> upperLocalBits];
+                    double2 own = make_double2(0.0, 0.0);
+                    if (lane < segLen) own = src[((static_cast<uint64_t>(c & localSegMask)) << S) + lane];
+                    const int kk = p.subK[sub];
+                    for (int k = 0; k < kk; ++k) {
+                        const int at = (sub * p.kMax + k) * 32 + lane;
+                        cmac(acc, cmul(we, p.subW[at]), shfl2(own, p.subCol[at]));
+                    }
+                }
+                accTile[j * 32 + lane] = acc;
+            }
+            __syncwarp();
+            if (__all_sync(0xffffffffu, done)) break;
+        }
+        for (int j = 0; j < nSegTile; ++j) {
+            if (lane < segLen) st_stream(p.z + (((static_cast<uint64_t>(tile) * 32u) + j) << S) + lane, accTile[j * 32 + lane]);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // DMAVM tile kernel (the fast path)
 // ------------------------------------------------------------------------------------------------
 // Precondition (checked on the host, gate_compile.cpp "tile bits"): every upper level with an

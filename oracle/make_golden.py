@@ -40,12 +40,12 @@ SMALL = {
     "mix_n12_f1": ("tests/circuits/mix_n12.qasm", 8, 1, ["--kat-gates", "1"]),
 }
 MEDIUM = {
-    "synth_n20_f1": (ROOT / "oracle/_ref/circuits/synth_n20.qasm", 8, 1, ["--no-kat", "--full-state"]),
-    "vqe_n16_f0": (REF / "circuits/vqe_n16.qasm", 8, 0, ["--kat-gates", "2", "--full-state"]),
-    "vqe_n16_f1": (REF / "circuits/vqe_n16.qasm", 8, 1, ["--kat-gates", "1", "--full-state"]),
-    "dnn_n16_f1": (REF / "circuits/dnn_n16.qasm", 8, 1, ["--kat-gates", "1", "--full-state"]),
+    "synth_n20_f1": (ROOT / "oracle/_ref/circuits/synth_n20.qasm", 8, 1, ["--no-kat", "--samples", "65536"]),
+    "vqe_n16_f0": (REF / "circuits/vqe_n16.qasm", 8, 0, ["--no-kat", "--full-state"]),
+    "vqe_n16_f1": (REF / "circuits/vqe_n16.qasm", 8, 1, ["--no-kat", "--full-state"]),
+    "dnn_n16_f1": (REF / "circuits/dnn_n16.qasm", 8, 1, ["--no-kat", "--full-state"]),
     "ghz_state_n23_f0": (REF / "circuits/ghz_state_n23.qasm", 8, 0, ["--no-kat"]),
-    "supremacy_n20_f1": (REF / "circuits/supremacy_n20.qasm", 8, 1, ["--no-kat", "--full-state"]),
+    "supremacy_n20_f1": (REF / "circuits/supremacy_n20.qasm", 8, 1, ["--no-kat", "--samples", "65536"]),
     "dnn_n20_f1": (REF / "circuits/dnn_n20.qasm", 8, 1, ["--no-kat"]),
 }
 LARGE = {

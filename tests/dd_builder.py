@@ -98,3 +98,17 @@ def controlled(u: np.ndarray, n_controls: int) -> np.ndarray:
         for c in range(1 << k):
             m[(r << n_controls) | mask, (c << n_controls) | mask] = u[r, c]
     return m
+
+
+def kron_dd(n: int, factors: dict) -> FlatDD:
+    """Tensor product of one-qubit matrices: factors[q] is the 2x2 matrix on qubit q (identity elsewhere).
+    One node per level, all four successors point to the node of the level below."""
+    level, child, weight = [], [], []
+    for lv in range(n - 1, -1, -1):
+        m = np.asarray(factors.get(lv, np.eye(2)), dtype=np.complex128)
+        nxt = len(level) + 1 if lv > 0 else TERMINAL
+        level.append(lv)
+        child.append([nxt if m[r, c] != 0 else TERMINAL for r in range(2) for c in range(2)])
+        weight.append([[m[r, c].real, m[r, c].imag] for r in range(2) for c in range(2)])
+    return FlatDD(n, 4, 0, np.array([1.0, 0.0]), np.array(level, dtype=np.int32), np.array(child, dtype=np.int32),
+                  np.array(weight, dtype=np.float64))

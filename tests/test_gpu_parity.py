@@ -165,6 +165,53 @@ def test_gate_shapes_vs_numpy_and_oracle(n, targets, kind):
         assert G.max_amp_err(re, im, orr, oi) < AMP_TOL
 
 
+@pytest.mark.parametrize("n,targets", [(12, [11, 10, 9, 8, 7, 6, 5]), (13, [12, 3, 11, 10, 9, 8, 7, 6]), (11, [5, 6, 7, 8, 9, 10])])
+def test_very_dense_gate_takes_the_chunk_kernel(n, targets):
+    """A block that is dense on many upper qubits (64-256 sources per output segment) exceeds the
+    resident lists of the tile and walk kernels; the chunk kernel must still give the exact product."""
+    rng = np.random.default_rng(n)
+    u = B.random_unitary(len(targets), rng)
+    gate = B.gate_dd(n, targets, u)
+    yr, yi = B.random_state(n, rng)
+    ref = B.apply_dense(n, targets, u, yr + 1j * yi)
+    with Context(n) as ctx:
+        ctx.set_state(yr, yi)
+        ctx.apply(gate)
+        re, im = ctx.get_state()
+    assert np.max(np.abs((re + 1j * im) - ref)) < 1e-12
+
+
+def test_512_paths_per_segment():
+    """Nine dense upper qubits = 512 source segments per output segment (the reference's own
+    --fuse 1 schedule produces such blocks on random circuits): only the chunk kernel holds that."""
+    n = 15
+    rng = np.random.default_rng(15)
+    factors = {q: B.random_unitary(1, rng) for q in range(5, 14)}
+    factors[2] = B.random_unitary(1, rng)
+    gate = B.kron_dd(n, factors)
+    yr, yi = B.random_state(n, rng)
+    psi = yr + 1j * yi
+    for q, m in factors.items():
+        psi = B.apply_dense(n, [q], m, psi)
+    with Context(n) as ctx:
+        ctx.set_state(yr, yi)
+        ctx.apply(gate)
+        re, im = ctx.get_state()
+    assert np.max(np.abs((re + 1j * im) - psi)) < 1e-12
+
+
+def test_chunk_kernel_forced_on_a_trace():
+    case = "mix_n12_f1"
+    n, records = read_trace(G.GOLDEN / case / "trace.bin")
+    orr, oi = pyoracle.replay_trace(records)
+    with Context(n) as ctx:
+        ctx.set_option("dmavm_variant", 9)
+        for rec in records:
+            (ctx.convert if rec.kind == 1 else ctx.apply)(rec.dd)
+        re, im = ctx.get_state()
+    assert G.max_amp_err(re, im, orr, oi) < 1e-13
+
+
 def test_zero_state_and_norm():
     with Context(11) as ctx:
         ctx.set_zero_state()
