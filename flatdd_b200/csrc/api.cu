@@ -175,6 +175,7 @@ template <int TB> Kernel tileKernelTB(int mode, int kt) {
         case 0: return dmavm_tile_kernel<TB, 0, 0>;
         case 1: return kt == 2 ? dmavm_tile_kernel<TB, 1, 2> : (kt == 4 ? dmavm_tile_kernel<TB, 1, 4> : dmavm_tile_kernel<TB, 1, 8>);
         case 2: return kt == 2 ? dmavm_tile_kernel<TB, 2, 2> : (kt == 4 ? dmavm_tile_kernel<TB, 2, 4> : dmavm_tile_kernel<TB, 2, 8>);
+        case 4: return kt == 2 ? dmavm_tile_kernel<TB, 4, 2> : (kt == 4 ? dmavm_tile_kernel<TB, 4, 4> : dmavm_tile_kernel<TB, 4, 8>);
         default:
             return kt == 2 ? dmavm_tile_kernel<TB, 3, 2>
                            : (kt == 4 ? dmavm_tile_kernel<TB, 3, 4> : (kt == 8 ? dmavm_tile_kernel<TB, 3, 8> : dmavm_tile_kernel<TB, 3, 0>));
@@ -243,14 +244,32 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
                 mode = h.maxPaths * (8 + 5 * kt) <= 9 * h.maxPaths + 8 * kt ? 1 : 2;
             } else {
                 mode = 3;
+                // per-sub entry lists when they fit the packed counters and the slot budget
+                int slots = 0;
+                bool fits = kt > 0 && h.nSub <= 8;
+                for (int ps : h.subPaths) {
+                    fits = fits && ps <= 15;
+                    slots += ps;
+                }
+                if (fits && slots <= 15 && c->forceMode == 4) mode = 4; // opt-in: measured slower than MODE 3 (padding)
             }
         }
-        if (c->forceMode >= 0 && !allIdentity && (c->forceMode == 3 || (h.nSub == 1 && kt > 0))) mode = c->forceMode;
+        if (c->forceMode >= 0 && c->forceMode <= 3 && !allIdentity && (c->forceMode == 3 || (h.nSub == 1 && kt > 0))) mode = c->forceMode;
         p.tileBits = h.tileBits;
         p.subTileBits = h.subTileBits;
         p.tileMask = h.tileMask;
         p.fillMask = h.fillMask;
         p.nTiles = p.nSeg >> h.tileBits;
+        p.uniform = h.uniform ? 1 : 0;
+        if (mode == 4) { // the entry area holds the concatenated per-sub lists
+            int slots = 0;
+            for (int sIdx = 0; sIdx < std::min(h.nSub, 8); ++sIdx) {
+                p.subBase[sIdx] = static_cast<uint8_t>(slots);
+                slots += h.subPaths[static_cast<size_t>(sIdx)];
+            }
+            for (int sIdx = std::min(h.nSub, 8); sIdx < 9; ++sIdx) p.subBase[sIdx] = static_cast<uint8_t>(slots);
+            p.maxPaths = std::max(slots, 1);
+        }
         const size_t perWarpT = tileWarpSmem(p.maxPaths, p.stackCap, h.subTileBits);
         const Kernel kernel = tileKernel(h.subTileBits, mode, kt);
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
@@ -702,7 +721,7 @@ int fdd_gate_free(fdd_gate* gate) {
 static long gateFact(const CompiledGate& h, const std::string& k) {
     if (k == "kind") return h.diagonal ? 1 : 0;
     if (k == "max_paths") return h.maxPaths;
-    if (k == "max_sub_k") return h.kMax;
+    if (k == "max_sub_k") return h.kTrue;
     if (k == "upper_nodes") return static_cast<long>(h.upper.size());
     if (k == "sub_tables") return h.nSub;
     if (k == "nnz_per_row_max") return h.nnzRowMax;
@@ -712,6 +731,7 @@ static long gateFact(const CompiledGate& h, const std::string& k) {
     if (k == "non_diag_mask") return static_cast<long>(h.nonDiagMask);
     if (k == "nnz") return static_cast<long>(h.nnz);
     if (k == "tileable") return h.tileable ? 1 : 0;
+    if (k == "uniform") return h.uniform ? 1 : 0;
     if (k == "sub_tile_bits") return h.subTileBits;
     if (k == "non_diag_upper") return h.nonDiagUpper;
     return -1;

@@ -298,6 +298,7 @@ CompiledGate compileGate(const fdd_matdd& g, int nLocal) {
         out.subK[static_cast<std::size_t>(s)] = k;
         out.kMax = std::max(out.kMax, k);
     }
+    out.kTrue = out.kMax;
     // pad the ELL width to 2, 4 or 8 so the kernels can unroll it without a bound check
     if (out.kMax <= 8) out.kMax = out.kMax <= 2 ? 2 : (out.kMax <= 4 ? 4 : 8);
     out.subCol.assign(static_cast<std::size_t>(out.nSub) * out.kMax * 32, 0);
@@ -357,11 +358,22 @@ CompiledGate compileGate(const fdd_matdd& g, int nLocal) {
             depth[idx] = dp;
         }
         out.maxPaths = std::max(1, P(out.root));
+        // the same bound per sub table (paths of one row that end in table s)
+        out.subPaths.assign(static_cast<std::size_t>(out.nSub), 0);
+        for (int sIdx = 0; sIdx < out.nSub; ++sIdx) {
+            std::vector<int> ps(nu, 0);
+            auto Ps = [&](int32_t code) { return code >= 0 ? ps[static_cast<std::size_t>(code)] : (code == encodeSub(sIdx) ? 1 : 0); };
+            for (std::size_t idx : order) {
+                const UpperNode& nd = out.upper[idx];
+                ps[idx] = std::min(1 << 20, std::max(Ps(nd.child[0]) + Ps(nd.child[1]), Ps(nd.child[2]) + Ps(nd.child[3])));
+            }
+            out.subPaths[static_cast<std::size_t>(sIdx)] = Ps(out.root);
+        }
         out.stackCap = std::max(1, St(out.root));
         out.upperDepth = Dp(out.root);
     }
     out.nnz = macCount(g);
-    out.nnzRowMax = out.maxPaths * out.kMax;
+    out.nnzRowMax = out.maxPaths * out.kTrue;
 
     // ---- tile bits -----------------------------------------------------------------------------------
     {
@@ -387,9 +399,11 @@ CompiledGate compileGate(const fdd_matdd& g, int nLocal) {
             out.tileMask = mask;
             out.fillMask = fill;
             out.subTileBits = out.nonDiagUpper;
+            out.uniform = true;
             for (UpperNode& nd : out.upper) {
                 const int sh = nd.level - S;
                 nd.slotBit = (sh < 32 && ((mask >> sh) & 1u)) ? __builtin_popcount(mask & ((1u << sh) - 1u)) : -1;
+                if (nd.slotBit < 0) out.uniform = false;
             }
         } else {
             for (UpperNode& nd : out.upper) nd.slotBit = -1;
@@ -407,7 +421,7 @@ double costGpuNs(const CompiledGate& c, double hbmGBs, double fp64GFlops) {
     const double amps = std::ldexp(1.0, c.n);
     const double memNs = 32.0 * amps / hbmGBs; // GB/s == B/ns
     const double flopNs = 14.0 * static_cast<double>(c.nnz) / fp64GFlops;
-    const double instrPerSeg = 40.0 + c.maxPaths * (14.0 + 16.0 * c.kMax) + 12.0 * c.upperDepth * c.maxPaths / 4.0;
+    const double instrPerSeg = 40.0 + c.maxPaths * (14.0 + 16.0 * c.kTrue) + 12.0 * c.upperDepth * c.maxPaths / 4.0;
     const double issueNs = (amps / 32.0) * instrPerSeg / (148.0 * 4.0 * 1.8 * 0.6);
     const double walkPenalty = c.tileable ? 1.0 : 3.0; // gates that do not tile take the walk kernel
     const double launchNs = 3000.0;

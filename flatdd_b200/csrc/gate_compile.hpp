@@ -48,13 +48,15 @@ struct CompiledGate {
     double rootW[2] = {0.0, 0.0};
     std::vector<UpperNode> upper;
     int nSub = 0;
-    int kMax = 0;                 // ELL width (max over sub tables)
+    int kMax = 0;                 // ELL width of the tables (max over sub tables, padded to 2, 4 or 8)
+    int kTrue = 0;                // largest number of non-zeros in one sub-table row
     std::vector<uint8_t> subCol;  // [nSub][kMax][32]
     std::vector<double> subW;     // [nSub][kMax][32][2]
     std::vector<int32_t> subK;    // [nSub] entries per row actually used
     std::vector<uint8_t> subFlags;
     // facts
     int maxPaths = 1;   // upper bound on source segments per output segment
+    std::vector<int> subPaths; // [nSub] upper bound on the paths of one row that end in sub table s
     int stackCap = 1;   // DFS stack bound for the upper walk
     int upperDepth = 0; // longest chain of upper nodes on a path (after compression)
     uint64_t nnz = 0;   // non-zero matrix entries
@@ -70,6 +72,7 @@ struct CompiledGate {
     uint32_t tileMask = 0; // index bits of the non-diagonal upper levels (a sub-tile is closed under the gate)
     uint32_t fillMask = 0; // lowest free index bits that complete the warp tile
     int nonDiagUpper = 0; // upper levels with an off-diagonal successor
+    bool uniform = false; // tileable and every upper node sits on a tile bit: all sub-tiles see the same entries
     uint64_t nonDiagMask = 0; // bit v set when level v has an off-diagonal successor (all levels)
 };
 

@@ -197,6 +197,9 @@ struct WalkParams {
     int subTileBits;                  // tile kernel: TB = number of bits in tileMask
     uint32_t tileMask;                // tile kernel: segment-index bits of the non-diagonal upper levels
     uint32_t fillMask;                // tile kernel: further index bits that complete the warp tile
+    // tile kernel MODE 4: entry lists kept per sub table; list s occupies slots [subBase[s], subBase[s+1])
+    uint8_t subBase[9];
+    int uniform;                      // tile kernel: the entry lists do not depend on the tile (walk once per warp)
 };
 
 // Bytes of shared memory one warp needs.
@@ -587,6 +590,8 @@ __global__ void __launch_bounds__(128) dmavm_chunk_kernel(const WalkParams p) {
 // MODE 2: one sub table L for the whole gate, shuffle last          z_j = L (sum_i w_ji y_slot(j,i))
 //         (the operator factorises as U (x) L; L lives in registers, KT entries per row)
 // MODE 3: sub table depends on the path, gather first               z_j = sum_i w_ji (L_sub(j,i) y_slot(j,i))
+// MODE 4: like MODE 3 but the entry lists are kept per sub table (at most 8 tables, 15 slots), so each
+//         table is applied once per output segment, shuffle last    z_j = sum_s L_s (sum_{i in s} w_ji y_slot(j,i))
 // KT = ELL width of the sub tables rounded up to 2, 4 or 8 (static unrolling); KT = 0 (MODE 3 only)
 // reads the width at run time.  The host picks MODE 1 or 2 by instruction count.
 template <int TB> struct TileShape {
@@ -724,7 +729,8 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
     for (uint32_t tile = warpGlobal; tile < p.nTiles; tile += warpStride) {
         const uint32_t base = depositAround(tile, wtMask);
         // =================== phase A: upper walk, lane = segment of the warp tile =================
-        if (lane < wtSegs) {
+        // (a gate whose upper nodes all sit on tile bits gives every tile the same lists: walk once)
+        if (lane < wtSegs && !(p.uniform && tile != warpGlobal)) {
             int cnt = 0;
             if (p.root != FDD_TERMINAL) {
                 const uint32_t rowSeg = rankBits | base | myDep;
@@ -768,10 +774,17 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
                         }
                     }
                     if (code <= -2) {
-                        const int at = cnt * 32 + lane;
+                        const int sub = -2 - code;
+                        int at;
+                        if (MODE == 4) { // per-sub list: 4-bit fill counters packed into cnt
+                            at = (p.subBase[sub] + ((cnt >> (4 * sub)) & 15)) * 32 + lane;
+                            cnt += 1 << (4 * sub);
+                        } else {
+                            at = cnt * 32 + lane;
+                            ++cnt;
+                        }
                         eW[at] = w;
-                        ePack[at] = slot | (static_cast<uint32_t>(-2 - code) << 8);
-                        ++cnt;
+                        ePack[at] = slot | (static_cast<uint32_t>(sub) << 8);
                     }
                     if (sp == 0) break;
                     --sp;
@@ -782,9 +795,19 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
                     code = static_cast<int>(pk << 8) >> 8; // sign-extend the 24-bit successor code
                 }
             }
-            for (int i = cnt; i < P; ++i) { // zero-weight padding
-                eW[i * 32 + lane] = make_double2(0.0, 0.0);
-                ePack[i * 32 + lane] = static_cast<uint32_t>(lane & (T - 1));
+            // zero-weight padding
+            if (MODE == 4) {
+                for (int sIdx = 0; sIdx < p.nSub; ++sIdx) {
+                    for (int i = p.subBase[sIdx] + ((cnt >> (4 * sIdx)) & 15); i < p.subBase[sIdx + 1]; ++i) {
+                        eW[i * 32 + lane] = make_double2(0.0, 0.0);
+                        ePack[i * 32 + lane] = static_cast<uint32_t>(lane & (T - 1));
+                    }
+                }
+            } else {
+                for (int i = cnt; i < P; ++i) {
+                    eW[i * 32 + lane] = make_double2(0.0, 0.0);
+                    ePack[i * 32 + lane] = static_cast<uint32_t>(lane & (T - 1));
+                }
             }
         }
         __syncwarp();
@@ -842,6 +865,28 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
 #pragma unroll
                             for (int k = 0; k < KR; ++k) cmac(t, Lw[k], src[Lc[k]]);
                             cmac(acc[a], w, t);
+                        }
+                    }
+                } else if (MODE == 4) {
+                    for (int sIdx = 0; sIdx < p.nSub; ++sIdx) {
+                        double2 u[NACC];
+#pragma unroll
+                        for (int a = 0; a < NACC; ++a) u[a] = make_double2(0.0, 0.0);
+                        for (int i = p.subBase[sIdx]; i < p.subBase[sIdx + 1]; ++i) {
+#pragma unroll
+                            for (int a = 0; a < NACC; ++a) {
+                                const double2 w = eW[i * 32 + rowBase + a];
+                                const uint32_t pk = ePack[i * 32 + rowBase + a];
+                                cmac(u[a], w, stageOf(a)[(pk & 31u) * 32 + lane]);
+                            }
+                        }
+                        const int at0 = sIdx * (KT > 0 ? KT : 1) * 32 + lane;
+#pragma unroll
+                        for (int k = 0; k < (KT > 0 ? KT : 1); ++k) {
+                            const double2 lw = subW[at0 + k * 32];
+                            const int lc = subCol[at0 + k * 32];
+#pragma unroll
+                            for (int a = 0; a < NACC; ++a) cmac(acc[a], lw, shfl2(u[a], lc));
                         }
                     }
                 } else {

@@ -18,6 +18,10 @@
 // What is new:
 //   * fuse == 3: the same greedy control flow driven by the GPU cost model (fdd_cost_gpu: one
 //     launch costs max(HBM time, fp64 time) and a bound on the DD size), see DESIGN.md;
+//   * fuse == 4: dependency-graph fusion.  Operations on disjoint qubits commute, so a block is grown
+//     from ALL operations whose predecessors are done (not just the next one in program order) as long
+//     as it stays a cheap launch: at most 2 dense qubits (<= 4 non-zeros per row), at most 5
+//     non-diagonal qubits above the warp lanes (it still tiles) and a bounded DD;
 //   * identity gates (barriers) are detected and not launched; no memsets; no scratch arrays;
 //   * the state lives on the device; getVector materialises host arrays lazily.
 //
@@ -28,6 +32,7 @@
 #include "array_backend.hpp"
 #include "flatten.hpp"
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstddef>
@@ -43,6 +48,11 @@ struct FusionPolicy {
     double hbmGBs = 6500.0;      // MEASURED_PEAKS.json hbm_gbs
     double fp64GFlops = 30000.0; // sustained fp64 FMA rate assumed by the cost model
     int maxNodes = 4096;         // bound on the flat table of a fused gate
+    // fuse == 4 (dependency-graph fusion): a block may hold at most this many dense qubits
+    // (non-zeros per row <= 2^maxDenseQubits) and this many non-diagonal qubits above the warp lanes
+    int maxDenseQubits = 2;
+    int maxTileQubits = 5;
+    double budgetFactor = 1.8;   // accept a block while its modelled time <= budgetFactor x the HBM time of one pass
 };
 
 template <class Package, class Qc, class DdOps, class WeightTraits> class GpuSwitchSimulator {
@@ -406,6 +416,7 @@ private:
     // Greedy schedule over ops[first..] up to the first non-unitary operation.
     // Control flow of src/SwitchSimulator.cpp:271-340 (fuse 1), :341-372 (fuse 2); fuse 3 swaps the cost.
     Schedule buildSchedule(std::size_t first) {
+        if (fuse == 4) return buildScheduleDag(first);
         Schedule s;
         const std::size_t nDim = std::size_t{1} << qc->getNqubits();
         const auto& ops = qc->ops;
@@ -486,6 +497,114 @@ private:
             std::cout << "Saved cost %: "
                       << 100 * static_cast<double>(savedComp) / static_cast<double>(totalComp == 0 ? 1 : totalComp) << "%"
                       << std::endl;
+        }
+        return s;
+    }
+
+    // Dependency-graph fusion (fuse == 4).  Two operations are ordered only if they share a qubit.
+    Schedule buildScheduleDag(std::size_t first) {
+        Schedule s;
+        const auto& ops = qc->ops;
+        std::size_t last = first;
+        while (last < ops.size() && !ops[last]->isNonUnitaryOperation()) ++last;
+        const std::size_t count = last - first;
+        if (verbose) std::cout << "Using dependency-graph merge with the GPU cost model... " << std::endl;
+        // last-writer dependencies per qubit
+        std::vector<std::vector<std::size_t>> succ(count);
+        std::vector<int> indeg(count, 0);
+        {
+            std::vector<long> lastOn(static_cast<std::size_t>(nq()), -1);
+            for (std::size_t i = 0; i < count; ++i) {
+                std::vector<long> preds;
+                for (int q : DdOps::allQubits(*ops[first + i])) {
+                    const long pOp = lastOn[static_cast<std::size_t>(q)];
+                    if (pOp >= 0) {
+                        bool dup = false;
+                        for (long x : preds) dup = dup || x == pOp;
+                        if (!dup) preds.push_back(pOp);
+                    }
+                    lastOn[static_cast<std::size_t>(q)] = static_cast<long>(i);
+                }
+                for (long pOp : preds) {
+                    succ[static_cast<std::size_t>(pOp)].push_back(i);
+                    ++indeg[i];
+                }
+            }
+        }
+        std::vector<std::size_t> ready; // kept sorted (program order)
+        for (std::size_t i = 0; i < count; ++i) {
+            if (indeg[i] == 0) ready.push_back(i);
+        }
+        const int local = worldSize > 1 ? nLocal() : nq();
+        const int laneBits = std::min(5, local);
+        const double memNs = 32.0 * std::ldexp(1.0, nq()) / policy.hbmGBs;
+        auto physical = [&](int logical) {
+            return worldSize > 1 ? static_cast<int>(perm[static_cast<typename Perm::key_type>(logical)]) : logical;
+        };
+        auto needsGlobal = [&](std::size_t i) {
+            if (worldSize <= 1 || DdOps::isRelabelSwap(*ops[first + i])) return false;
+            for (int q : DdOps::nonDiagonalQubits(*ops[first + i])) {
+                if (physical(q) >= local) return true;
+            }
+            return false;
+        };
+        std::size_t done = 0;
+        while (done < count) {
+            // sharded: if nothing ready is executable under the current layout, remap for the earliest ready operation
+            if (worldSize > 1) {
+                bool any = false;
+                for (std::size_t i : ready) any = any || !needsGlobal(i);
+                if (!any) s.queueExchanges(planExchanges(first + ready.front()));
+            }
+            auto current = dd->makeIdent(qc->getNqubits());
+            int currentCount = 0;
+            std::vector<int> dense, tile; // physical positions
+            bool progress = true;
+            while (progress) {
+                progress = false;
+                for (std::size_t r = 0; r < ready.size(); ++r) {
+                    const std::size_t i = ready[r];
+                    const auto* op = ops[first + i].get();
+                    if (needsGlobal(i)) continue;
+                    // symbolic pre-check on the physical qubit sets
+                    std::vector<int> newDense = dense, newTile = tile;
+                    if (!(worldSize > 1 && DdOps::isRelabelSwap(*op))) {
+                        for (int q : DdOps::denseQubits(*op)) {
+                            const int pq = physical(q);
+                            bool have = false;
+                            for (int x : newDense) have = have || x == pq;
+                            if (!have) newDense.push_back(pq);
+                        }
+                        for (int q : DdOps::nonDiagonalQubits(*op)) {
+                            const int pq = physical(q);
+                            if (pq < laneBits) continue;
+                            bool have = false;
+                            for (int x : newTile) have = have || x == pq;
+                            if (!have) newTile.push_back(pq);
+                        }
+                    }
+                    if (static_cast<int>(newDense.size()) > policy.maxDenseQubits || static_cast<int>(newTile.size()) > policy.maxTileQubits) continue;
+                    auto next = gateFor(op, &s.pending);
+                    auto candidate = dd->multiply(next, current);
+                    if (currentCount > 0) { // a block of one operation is always allowed
+                        const Cost c = gpuCost(candidate);
+                        if (static_cast<double>(c.value) - 3000.0 > policy.budgetFactor * memNs) continue; // 3000 ns = launch term of the model
+                    }
+                    current = candidate;
+                    ++currentCount;
+                    dense.swap(newDense);
+                    tile.swap(newTile);
+                    ready.erase(ready.begin() + static_cast<long>(r));
+                    for (std::size_t nxt : succ[i]) {
+                        if (--indeg[nxt] == 0) ready.insert(std::lower_bound(ready.begin(), ready.end(), nxt), nxt);
+                    }
+                    ++done;
+                    progress = true;
+                    break; // rescan from the earliest ready operation
+                }
+            }
+            if (currentCount == 0) throw std::runtime_error("dependency-graph fusion made no progress");
+            s.push(current, currentCount, false);
         }
         return s;
     }

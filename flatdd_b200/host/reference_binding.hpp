@@ -57,6 +57,40 @@ struct RefDdOps {
         for (const auto t : op.getTargets()) out.push_back(static_cast<int>(t));
         return out;
     }
+    // targets on which the operation is dense (neither diagonal nor a permutation with phases): these
+    // double the non-zeros per row of a fused block; X/Y/SWAP/iSWAP/DCX targets only move amplitudes
+    static std::vector<int> denseQubits(const qc::Operation& op) {
+        std::vector<int> out;
+        if (op.isNonUnitaryOperation()) return out;
+        if (const auto* compound = dynamic_cast<const qc::CompoundOperation*>(&op)) {
+            for (const auto& sub : *compound) {
+                for (int q : denseQubits(*sub)) out.push_back(q);
+            }
+            return out;
+        }
+        switch (op.getType()) {
+            case qc::I: case qc::Z: case qc::S: case qc::Sdag: case qc::T: case qc::Tdag: case qc::Phase: case qc::RZ:
+            case qc::RZZ: case qc::GPhase: case qc::Barrier: case qc::X: case qc::Y: case qc::SWAP: case qc::iSWAP: case qc::DCX:
+                return out;
+            default:
+                break;
+        }
+        for (const auto t : op.getTargets()) out.push_back(static_cast<int>(t));
+        return out;
+    }
+    // every qubit the operation touches (targets and controls)
+    static std::vector<int> allQubits(const qc::Operation& op) {
+        std::vector<int> out;
+        if (const auto* compound = dynamic_cast<const qc::CompoundOperation*>(&op)) {
+            for (const auto& sub : *compound) {
+                for (int q : allQubits(*sub)) out.push_back(q);
+            }
+            return out;
+        }
+        for (const auto t : op.getTargets()) out.push_back(static_cast<int>(t));
+        for (const auto& c : op.getControls()) out.push_back(static_cast<int>(c.qubit));
+        return out;
+    }
     static bool isMeasure(const qc::Operation& op) { return op.getType() == qc::Measure; }
     static bool isBarrier(const qc::Operation& op) { return op.getType() == qc::Barrier; }
     static bool isReset(const qc::Operation& op) { return op.getType() == qc::Reset; }

@@ -19,6 +19,19 @@ def gate_dd(n: int, targets, matrix: np.ndarray, tol: float = 0.0) -> FlatDD:
     pos = {q: i for i, q in enumerate(targets)}
     level, child, weight = [], [], []
     unique = {}
+    lowest = min(targets)
+
+    def ident_chain(lv: int) -> int:
+        if lv < 0:
+            return TERMINAL
+        key = ("ident", lv)
+        if key not in unique:
+            below = ident_chain(lv - 1)
+            unique[key] = len(level)
+            level.append(lv)
+            child.append([below, TERMINAL, TERMINAL, below])
+            weight.append([[1.0, 0.0], [0.0, 0.0], [0.0, 0.0], [1.0, 0.0]])
+        return unique[key]
 
     def make(lv: int, rows: tuple, cols: tuple):
         """DD of the sub-matrix with the dense bits of levels > lv already fixed (rows/cols are
@@ -28,9 +41,11 @@ def gate_dd(n: int, targets, matrix: np.ndarray, tol: float = 0.0) -> FlatDD:
         free = [pos[q] for q in targets if q <= lv]
         ridx = sum(v << b for b, v in rfix.items())
         cidx = sum(v << b for b, v in cfix.items())
-        if lv < 0:
+        if lv < lowest:
+            # below the lowest target everything is identity: one shared chain with unit weights, the
+            # matrix entry sits on the edge into it (weights live near the top, as in a normalised DD)
             val = matrix[ridx, cidx]
-            return (TERMINAL, complex(val)) if abs(val) > tol else (TERMINAL, 0j)
+            return (ident_chain(lv), complex(val)) if abs(val) > tol else (TERMINAL, 0j)
         # zero test on the whole remaining block
         sub = matrix
         r_sel = [ridx + sum(((m >> i) & 1) << b for i, b in enumerate(free)) for m in range(1 << len(free))]
