@@ -100,6 +100,7 @@ struct fdd_ctx {
     int ctasPerSm = 0; // 0 = as many as shared memory allows (capped)
     int prefetch = 8;
     int forceMode = -1;   // experiments: force the tile-kernel MODE (1, 2 or 3) where it applies
+    int denseSlots = 1;   // experiments: 0 disables the dense register path of the tile kernel
     int exchangeUnroll = 8;
     int exchangeCtasPerSm = 4;
     // scratch
@@ -261,6 +262,9 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
         p.fillMask = h.fillMask;
         p.nTiles = p.nSeg >> h.tileBits;
         p.uniform = h.uniform ? 1 : 0;
+        const int tSegs = 1 << h.subTileBits;
+        p.denseSlots = ((mode == 0 || mode == 2) && tSegs >= 4 && tSegs <= 16 && tSegs <= 2 * h.maxPaths && c->denseSlots) ? 1 : 0;
+        if (p.denseSlots) p.maxPaths = std::max(p.maxPaths, tSegs); // the entry area holds one slot per source segment
         if (mode == 4) { // the entry area holds the concatenated per-sub lists
             int slots = 0;
             for (int sIdx = 0; sIdx < std::min(h.nSub, 8); ++sIdx) {
@@ -473,6 +477,7 @@ int fdd_set_option(fdd_ctx* ctx, const char* key, long value) {
         else if (k == "ctas_per_sm") ctx->ctasPerSm = static_cast<int>(value);
         else if (k == "prefetch") ctx->prefetch = static_cast<int>(value);
         else if (k == "tile_mode") ctx->forceMode = static_cast<int>(value);
+        else if (k == "dense_slots") ctx->denseSlots = static_cast<int>(value);
         else if (k == "exchange_unroll") ctx->exchangeUnroll = static_cast<int>(value);
         else if (k == "exchange_ctas_per_sm") ctx->exchangeCtasPerSm = static_cast<int>(value);
         else throw std::invalid_argument("unknown option " + k);
@@ -732,6 +737,8 @@ static long gateFact(const CompiledGate& h, const std::string& k) {
     if (k == "nnz") return static_cast<long>(h.nnz);
     if (k == "tileable") return h.tileable ? 1 : 0;
     if (k == "uniform") return h.uniform ? 1 : 0;
+    if (k == "tile_mask") return static_cast<long>(h.tileMask);
+    if (k == "fill_mask") return static_cast<long>(h.fillMask);
     if (k == "sub_tile_bits") return h.subTileBits;
     if (k == "non_diag_upper") return h.nonDiagUpper;
     return -1;

@@ -372,6 +372,8 @@ CompiledGate compileGate(const fdd_matdd& g, int nLocal) {
         out.stackCap = std::max(1, St(out.root));
         out.upperDepth = Dp(out.root);
     }
+    out.allIdentitySubs = true;
+    for (uint8_t f : out.subFlags) out.allIdentitySubs = out.allIdentitySubs && (f & SUB_IDENTITY);
     out.nnz = macCount(g);
     out.nnzRowMax = out.maxPaths * out.kTrue;
 
@@ -413,19 +415,34 @@ CompiledGate compileGate(const fdd_matdd& g, int nLocal) {
 }
 
 double costGpuNs(const CompiledGate& c, double hbmGBs, double fp64GFlops) {
-    // One launch costs max(HBM time, fp64 time, issue time).  Measured on B200 at n = 26 (profiles/r01_*):
-    // paths*K <= 4 runs at the HBM bound (0.37 ms), paths*K = 8 at 0.63 ms.  The issue term is kept
-    // deliberately pessimistic (it prices paths*K = 8 at ~0.9 ms): the greedy pass is myopic, and an
-    // accurate price makes it spend the dense budget early — the measured circuit time was 133 ms
-    // with the accurate model against 118 ms with this one (supremacy_n26, 216 vs 265 launches).
+    // Time of one launch as a multiple of the HBM time of one read + one write pass (0.33 ms at n = 26).
+    // Two regimes, both fitted to the tile kernel on B200 (profiles/r01_cost_model_fit.txt):
+    //  * KNOWN-FAST classes — the block does not depend on qubits outside its tile ("uniform"), its low
+    //    levels are untouched or one sub table serves the whole gate, and its upper part is either small
+    //    (<= 4 sources per segment) or complete (2^TB sources, TB <= 4: the register path).  Measured
+    //    0.40 / 0.44 / 0.52 ms at 4 / 8 / 16 sources, plus the cross-lane part.
+    //  * everything else — a deliberately pessimistic issue model (it prices 8 non-zeros per row at
+    //    ~2.7 passes).  The greedy pass is myopic: with an accurate price for the slow classes it
+    //    spends its dense budget early and ends up slower (measured 133 ms against 118 ms on
+    //    supremacy_n26), and the slow classes vary a lot (a sub table per path, long walks).
+    (void)fp64GFlops;
     const double amps = std::ldexp(1.0, c.n);
     const double memNs = 32.0 * amps / hbmGBs; // GB/s == B/ns
-    const double flopNs = 14.0 * static_cast<double>(c.nnz) / fp64GFlops;
-    const double instrPerSeg = 40.0 + c.maxPaths * (14.0 + 16.0 * c.kTrue) + 12.0 * c.upperDepth * c.maxPaths / 4.0;
-    const double issueNs = (amps / 32.0) * instrPerSeg / (148.0 * 4.0 * 1.8 * 0.6);
-    const double walkPenalty = c.tileable ? 1.0 : 3.0; // gates that do not tile take the walk kernel
+    const bool registerPath = c.tileable && c.subTileBits >= 2 && c.subTileBits <= 4 && (1 << c.subTileBits) <= 2 * c.maxPaths;
+    const bool knownFast = c.tileable && c.uniform && (c.allIdentitySubs || c.nSub == 1) &&
+                           c.kTrue <= (c.maxPaths > 4 ? 4 : 8) && (registerPath || c.maxPaths <= 4);
+    double factor;
+    if (knownFast) {
+        factor = 1.2 + (registerPath ? 0.025 * (1 << c.subTileBits) : 0.0);
+        if (c.kTrue > 1) factor += 0.035 * c.kTrue * std::max(1.0, c.maxPaths / 4.0); // (16,2): +0.28, (16,4): +0.56 measured
+    } else {
+        const double instrPerSeg = 40.0 + c.maxPaths * (14.0 + 16.0 * c.kTrue) + 12.0 * c.upperDepth * c.maxPaths / 4.0;
+        const double issueNs = (amps / 32.0) * instrPerSeg / (148.0 * 4.0 * 1.8 * 0.6);
+        factor = std::max(1.0, issueNs / memNs);
+        if (!c.tileable) factor *= 3.0; // walk kernel
+    }
     const double launchNs = 3000.0;
-    return walkPenalty * std::max(memNs, std::max(flopNs, issueNs)) + launchNs;
+    return factor * memNs + launchNs;
 }
 
 } // namespace fddb200

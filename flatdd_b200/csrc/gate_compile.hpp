@@ -63,6 +63,7 @@ struct CompiledGate {
     int nnzRowMax = 0;  // upper bound on non-zeros in one row (maxPaths * kMax)
     int topLevel = -1;  // highest level with a non-identity node (-1: scalar multiple of identity)
     bool diagonal = false; // every level diagonal
+    bool allIdentitySubs = false; // the low S levels are untouched on every path
     // tile-staged launch: the 2^tileBits segments of a tile differ in the index bits `tileMask`
     // (positions relative to the segment index).  Valid when every upper level that is not
     // diagonal fits into the tile, so that all sources of a tile lie in the tile itself.

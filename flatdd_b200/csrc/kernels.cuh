@@ -200,6 +200,7 @@ struct WalkParams {
     // tile kernel MODE 4: entry lists kept per sub table; list s occupies slots [subBase[s], subBase[s+1])
     uint8_t subBase[9];
     int uniform;                      // tile kernel: the entry lists do not depend on the tile (walk once per warp)
+    int denseSlots;                   // tile kernel: entries are stored by source slot (T per row, zero weight when absent)
 };
 
 // Bytes of shared memory one warp needs.
@@ -670,6 +671,12 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
     double2* ring = reinterpret_cast<double2*>(mine + static_cast<size_t>(nSlotsE) * 32 * 20);    // [R][T][32]
     const int stackBase = p.maxPaths;
     const int P = p.maxPaths;
+    // Dense register path (MODE 0 / 2: weights do not depend on the lane; 4..16 segments per sub-tile):
+    // phase A stores the entries of a row by source slot (zero weight where the matrix has none), so the
+    // T inputs of a sub-tile are loaded into registers once and every output is T FMAs against them,
+    // without per-entry slot lookups.  The host enables it when T <= 2 * maxPaths.
+    constexpr bool DENSE_OK = (MODE == 0 || MODE == 2) && T >= 4 && T <= 16;
+    const bool denseTile = DENSE_OK && p.denseSlots != 0;
 
     const uint32_t warpGlobal = blockIdx.x * warpsPerCta + warp;
     const uint32_t warpStride = gridDim.x * warpsPerCta;
@@ -732,6 +739,9 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
         // (a gate whose upper nodes all sit on tile bits gives every tile the same lists: walk once)
         if (lane < wtSegs && !(p.uniform && tile != warpGlobal)) {
             int cnt = 0;
+            if (DENSE_OK && p.denseSlots) {
+                for (int i = 0; i < T; ++i) eW[i * 32 + lane] = make_double2(0.0, 0.0);
+            }
             if (p.root != FDD_TERMINAL) {
                 const uint32_t rowSeg = rankBits | base | myDep;
                 const int tl = lane & (T - 1);
@@ -779,6 +789,8 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
                         if (MODE == 4) { // per-sub list: 4-bit fill counters packed into cnt
                             at = (p.subBase[sub] + ((cnt >> (4 * sub)) & 15)) * 32 + lane;
                             cnt += 1 << (4 * sub);
+                        } else if (DENSE_OK && p.denseSlots) {
+                            at = static_cast<int>(slot) * 32 + lane; // one entry per (row, source slot)
                         } else {
                             at = cnt * 32 + lane;
                             ++cnt;
@@ -803,7 +815,7 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
                         ePack[i * 32 + lane] = static_cast<uint32_t>(lane & (T - 1));
                     }
                 }
-            } else {
+            } else if (!(DENSE_OK && p.denseSlots)) {
                 for (int i = cnt; i < P; ++i) {
                     eW[i * 32 + lane] = make_double2(0.0, 0.0);
                     ePack[i * 32 + lane] = static_cast<uint32_t>(lane & (T - 1));
@@ -811,7 +823,6 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
             }
         }
         __syncwarp();
-
         // =================== phase B: stream the sub-tiles, lane = amplitude ========================
         // G consecutive sub-tiles are computed together so that at least four output segments
         // (independent FMA chains) are in flight even when a sub-tile is one or two segments
@@ -834,12 +845,26 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
                     return ring + slot * T * 32;
                 };
                 if (MODE == 0 || MODE == 2) {
-                    for (int i = 0; i < P; ++i) {
+                    if (DENSE_OK && denseTile) {
+                        // inputs of the sub-tile in registers (G == 1 here: one ring slot)
+                        constexpr int TD = DENSE_OK ? T : 1;
+                        double2 yv[TD];
+                        const double2* st = ring + useSlot * T * 32;
 #pragma unroll
-                        for (int a = 0; a < NACC; ++a) {
-                            const double2 w = eW[i * 32 + rowBase + a];
-                            const uint32_t pk = ePack[i * 32 + rowBase + a];
-                            cmac(acc[a], w, stageOf(a)[(pk & 31u) * 32 + lane]);
+                        for (int i = 0; i < TD; ++i) yv[i] = st[i * 32 + lane];
+#pragma unroll
+                        for (int i = 0; i < TD; ++i) {
+#pragma unroll
+                            for (int a = 0; a < NACC; ++a) cmac(acc[a], eW[i * 32 + rowBase + a], yv[i]);
+                        }
+                    } else {
+                        for (int i = 0; i < P; ++i) {
+#pragma unroll
+                            for (int a = 0; a < NACC; ++a) {
+                                const double2 w = eW[i * 32 + rowBase + a];
+                                const uint32_t pk = ePack[i * 32 + rowBase + a];
+                                cmac(acc[a], w, stageOf(a)[(pk & 31u) * 32 + lane]);
+                            }
                         }
                     }
                     if (MODE == 2) {
