@@ -274,14 +274,15 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
             for (int sIdx = std::min(h.nSub, 8); sIdx < 9; ++sIdx) p.subBase[sIdx] = static_cast<uint8_t>(slots);
             p.maxPaths = std::max(slots, 1);
         }
-        const size_t perWarpT = tileWarpSmem(p.maxPaths, p.stackCap, h.subTileBits);
+        const size_t perWarpT = tileWarpSmem(p.maxPaths, p.stackCap, h.subTileBits, p.uniform);
+        const size_t fixedT = fixed + tileCtaSmem(p.maxPaths, p.stackCap, p.uniform);
         const Kernel kernel = tileKernel(h.subTileBits, mode, kt);
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
         // pick the CTA width that keeps the most warps resident (registers and shared memory both count)
         int bestW = 0, bestC = 0;
         for (int w = 8; w >= 1; --w) {
             if (c->warpsPerCta > 0 && w > c->warpsPerCta) continue;
-            const size_t smemW = fixed + static_cast<size_t>(w) * perWarpT;
+            const size_t smemW = fixedT + static_cast<size_t>(w) * perWarpT;
             if (smemW > kSmemBudget) continue;
             int resident = 0;
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, w * 32, smemW));
@@ -292,7 +293,7 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
             }
         }
         if (bestW > 0) {
-            const size_t smemT = fixed + static_cast<size_t>(bestW) * perWarpT;
+            const size_t smemT = fixedT + static_cast<size_t>(bestW) * perWarpT;
             const uint32_t ctasWantedT = (p.nTiles + bestW - 1) / bestW;
             const int gridT = static_cast<int>(std::max<uint32_t>(1, std::min<uint32_t>(ctasWantedT, static_cast<uint32_t>(c->smCount * bestC))));
             Timed t(c);

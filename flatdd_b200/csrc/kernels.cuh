@@ -600,11 +600,19 @@ template <int TB> struct TileShape {
     static constexpr int R = (16 / T) < 2 ? 2 : (16 / T);
     static constexpr int JC = T < 8 ? T : 8;
 };
-__host__ __device__ inline size_t tileWarpSmem(int maxPaths, int stackCap, int tileBits) {
+// Shared memory of the tile kernel: the entry area (lists + walk stack) and the stage ring.  A uniform
+// gate gives every tile the same lists, so one entry area serves the whole CTA and only the ring is
+// per warp; otherwise every warp has its own entry area.
+__host__ __device__ inline size_t tileEntryBytes(int maxPaths, int stackCap) { return static_cast<size_t>(maxPaths + stackCap) * 32 * 20; }
+__host__ __device__ inline size_t tileRingBytes(int tileBits) {
     const int T = 1 << tileBits;
     const int R = (16 / T) < 2 ? 2 : (16 / T);
-    return static_cast<size_t>(maxPaths + stackCap) * 32 * 20 + static_cast<size_t>(R) * T * 512;
+    return static_cast<size_t>(R) * T * 512;
 }
+__host__ __device__ inline size_t tileWarpSmem(int maxPaths, int stackCap, int tileBits, int uniform) {
+    return tileRingBytes(tileBits) + (uniform ? 0 : tileEntryBytes(maxPaths, stackCap));
+}
+__host__ __device__ inline size_t tileCtaSmem(int maxPaths, int stackCap, int uniform) { return uniform ? tileEntryBytes(maxPaths, stackCap) : 0; }
 
 __device__ __forceinline__ uint32_t depositBits(uint32_t x, uint32_t mask) { // pdep
     uint32_t out = 0;
@@ -664,11 +672,14 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int warpsPerCta = blockDim.x >> 5;
-    unsigned char* mine = cursor + static_cast<size_t>(warp) * tileWarpSmem(p.maxPaths, p.stackCap, TB);
+    unsigned char* ctaEntries = cursor;
+    cursor += tileCtaSmem(p.maxPaths, p.stackCap, p.uniform);
+    unsigned char* mine = cursor + static_cast<size_t>(warp) * tileWarpSmem(p.maxPaths, p.stackCap, TB, p.uniform);
+    unsigned char* entries = p.uniform ? ctaEntries : mine;
     const int nSlotsE = p.maxPaths + p.stackCap;
-    double2* eW = reinterpret_cast<double2*>(mine);                                               // [nSlotsE][32]
-    uint32_t* ePack = reinterpret_cast<uint32_t*>(mine + static_cast<size_t>(nSlotsE) * 32 * 16); // [nSlotsE][32]
-    double2* ring = reinterpret_cast<double2*>(mine + static_cast<size_t>(nSlotsE) * 32 * 20);    // [R][T][32]
+    double2* eW = reinterpret_cast<double2*>(entries);                                               // [nSlotsE][32]
+    uint32_t* ePack = reinterpret_cast<uint32_t*>(entries + static_cast<size_t>(nSlotsE) * 32 * 16); // [nSlotsE][32]
+    double2* ring = reinterpret_cast<double2*>(p.uniform ? mine : mine + tileEntryBytes(p.maxPaths, p.stackCap)); // [R][T][32]
     const int stackBase = p.maxPaths;
     const int P = p.maxPaths;
     // Dense register path (MODE 0 / 2: weights do not depend on the lane; 4..16 segments per sub-tile):
@@ -692,8 +703,6 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
     const uint32_t myDep = depositBits(static_cast<uint32_t>(lane) & (T - 1), p.tileMask) |
                            depositBits(static_cast<uint32_t>(lane) >> TB, p.fillMask);
     const uint32_t rankBits = p.rank << upperLocalBits;
-    if (warpGlobal >= p.nTiles) return;
-
     // MODE 1/2: the single sub table lives in registers
     constexpr int KR = (MODE == 1 || MODE == 2) ? (KT > 0 ? KT : 1) : 1;
     double2 Lw[KR];
@@ -706,38 +715,9 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
         }
     }
 
-    // ---- copy pipeline state: running sub-tile counter over all warp tiles of this warp ---------
-    uint32_t issueTile = warpGlobal;
-    uint32_t issueBase = depositAround(issueTile, wtMask);
-    int issueQ = 0;
-    int issueSlot = 0;
-    auto issueNext = [&]() {
-        if (issueTile < p.nTiles) {
-#pragma unroll
-            for (int t = 0; t < T; ++t) {
-                const uint32_t dep = __shfl_sync(0xffffffffu, myDep, (issueQ << TB) | t);
-                if (lane < segLen) {
-                    cp_async16(ring + (issueSlot * T + t) * 32 + lane, p.y + ((static_cast<uint64_t>(issueBase | dep)) << S) + lane);
-                }
-            }
-            issueSlot = (issueSlot + 1 == R) ? 0 : issueSlot + 1;
-            if (++issueQ == Q) {
-                issueQ = 0;
-                issueTile += warpStride;
-                issueBase = depositAround(issueTile, wtMask);
-            }
-        }
-        cp_async_commit(); // one group per call (possibly empty) keeps the wait arithmetic uniform
-    };
-#pragma unroll
-    for (int r = 0; r < R; ++r) issueNext();
-    int useSlot = 0;
-
-    for (uint32_t tile = warpGlobal; tile < p.nTiles; tile += warpStride) {
-        const uint32_t base = depositAround(tile, wtMask);
-        // =================== phase A: upper walk, lane = segment of the warp tile =================
-        // (a gate whose upper nodes all sit on tile bits gives every tile the same lists: walk once)
-        if (lane < wtSegs && !(p.uniform && tile != warpGlobal)) {
+    // =================== phase A: upper walk, lane = segment of the warp tile =====================
+    auto walkTile = [&](uint32_t base) {
+        if (lane < wtSegs) {
             int cnt = 0;
             if (DENSE_OK && p.denseSlots) {
                 for (int i = 0; i < T; ++i) eW[i * 32 + lane] = make_double2(0.0, 0.0);
@@ -822,6 +802,44 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
                 }
             }
         }
+    };
+    if (p.uniform) {
+        // every tile sees the same lists: warp 0 walks once for the whole CTA
+        if (warp == 0) walkTile(0u);
+        __syncthreads();
+    }
+    if (warpGlobal >= p.nTiles) return;
+
+    // ---- copy pipeline state: running sub-tile counter over all warp tiles of this warp ---------
+    uint32_t issueTile = warpGlobal;
+    uint32_t issueBase = depositAround(issueTile, wtMask);
+    int issueQ = 0;
+    int issueSlot = 0;
+    auto issueNext = [&]() {
+        if (issueTile < p.nTiles) {
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const uint32_t dep = __shfl_sync(0xffffffffu, myDep, (issueQ << TB) | t);
+                if (lane < segLen) {
+                    cp_async16(ring + (issueSlot * T + t) * 32 + lane, p.y + ((static_cast<uint64_t>(issueBase | dep)) << S) + lane);
+                }
+            }
+            issueSlot = (issueSlot + 1 == R) ? 0 : issueSlot + 1;
+            if (++issueQ == Q) {
+                issueQ = 0;
+                issueTile += warpStride;
+                issueBase = depositAround(issueTile, wtMask);
+            }
+        }
+        cp_async_commit(); // one group per call (possibly empty) keeps the wait arithmetic uniform
+    };
+#pragma unroll
+    for (int r = 0; r < R; ++r) issueNext();
+    int useSlot = 0;
+
+    for (uint32_t tile = warpGlobal; tile < p.nTiles; tile += warpStride) {
+        const uint32_t base = depositAround(tile, wtMask);
+        if (!p.uniform) walkTile(base);
         __syncwarp();
         // =================== phase B: stream the sub-tiles, lane = amplitude ========================
         // G consecutive sub-tiles are computed together so that at least four output segments
