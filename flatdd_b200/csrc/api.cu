@@ -9,7 +9,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <stdexcept>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -107,6 +109,7 @@ struct fdd_ctx {
     double* dPartial = nullptr;
     double* dNorm = nullptr;
     std::vector<int32_t> logicalToPhysical;
+    std::map<std::tuple<const void*, size_t, size_t, int, int>, std::pair<int, int>> launchShapes; // tile-kernel CTA shapes
     // multi-GPU
     const double2* peerBuf[2][kMaxPeers] = {}; // state buffers of every rank (own ones included), mapped through CUDA IPC
     ncclComm_t comm = nullptr;
@@ -277,20 +280,29 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
         const size_t perWarpT = tileWarpSmem(p.maxPaths, p.stackCap, h.subTileBits, p.uniform);
         const size_t fixedT = fixed + tileCtaSmem(p.maxPaths, p.stackCap, p.uniform);
         const Kernel kernel = tileKernel(h.subTileBits, mode, kt);
-        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
-        // pick the CTA width that keeps the most warps resident (registers and shared memory both count)
+        // pick the CTA width that keeps the most warps resident (registers and shared memory both count);
+        // the answer only depends on (kernel, shared memory shape), so it is cached per context
         int bestW = 0, bestC = 0;
-        for (int w = 8; w >= 1; --w) {
-            if (c->warpsPerCta > 0 && w > c->warpsPerCta) continue;
-            const size_t smemW = fixedT + static_cast<size_t>(w) * perWarpT;
-            if (smemW > kSmemBudget) continue;
-            int resident = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, w * 32, smemW));
-            if (c->ctasPerSm > 0) resident = std::min(resident, c->ctasPerSm);
-            if (resident * w > bestW * bestC) {
-                bestW = w;
-                bestC = resident;
+        const auto key = std::make_tuple(reinterpret_cast<const void*>(kernel), fixedT, perWarpT, c->warpsPerCta, c->ctasPerSm);
+        const auto hit = c->launchShapes.find(key);
+        if (hit != c->launchShapes.end()) {
+            bestW = hit->second.first;
+            bestC = hit->second.second;
+        } else {
+            CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
+            for (int w = 8; w >= 1; --w) {
+                if (c->warpsPerCta > 0 && w > c->warpsPerCta) continue;
+                const size_t smemW = fixedT + static_cast<size_t>(w) * perWarpT;
+                if (smemW > kSmemBudget) continue;
+                int resident = 0;
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, w * 32, smemW));
+                if (c->ctasPerSm > 0) resident = std::min(resident, c->ctasPerSm);
+                if (resident * w > bestW * bestC) {
+                    bestW = w;
+                    bestC = resident;
+                }
             }
+            c->launchShapes.emplace(key, std::make_pair(bestW, bestC));
         }
         if (bestW > 0) {
             const size_t smemT = fixedT + static_cast<size_t>(bestW) * perWarpT;
@@ -390,6 +402,13 @@ fdd_ctx* createCtx(int nQubits, int device, int rank, int world) {
                             "; this library is built for sm_100a only");
         }
         CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        {
+            // gate tables come from the stream-ordered pool: keep freed blocks cached across synchronisations
+            cudaMemPool_t pool = nullptr;
+            CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+            uint64_t keep = ~uint64_t{0};
+            CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
         CUDA_TRY(cudaEventCreate(&ctx->ev0));
         CUDA_TRY(cudaEventCreate(&ctx->ev1));
         const size_t bytes = sizeof(double2) << ctx->nLocal;

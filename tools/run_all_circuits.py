@@ -1,0 +1,35 @@
+"""Runs build/flatdd_gpu on every reference circuit present under oracle/_ref/circuits and prints
+one JSON line per circuit (the CLI's own statistics block).  usage: python tools/run_all_circuits.py [fuse]"""
+import json
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+CLI = ROOT / "build" / "flatdd_gpu"
+fuse = sys.argv[1] if len(sys.argv) > 1 else "3"
+names = ["ghz_state_n23", "vqe_n16", "dnn_n16", "dnn_n20", "supremacy_n20", "supremacy_n24", "knn_n25", "swap_test_n25", "dnn_n25",
+         "supremacy_n26", "adder_n28", "knn_n31"]
+for name in names:
+    circuit = ROOT / "oracle" / "_ref" / "circuits" / f"{name}.qasm"
+    if not circuit.exists():
+        continue
+    with tempfile.TemporaryDirectory() as tmp:
+        cwd = Path(tmp) / "build" / "apps"
+        cwd.mkdir(parents=True)
+        (Path(tmp) / "log" / "results" / "time").mkdir(parents=True)
+        (Path(tmp) / "log" / "results" / "state").mkdir(parents=True)
+        t0 = time.perf_counter()
+        f = "0" if name.startswith("knn_n31") else fuse  # cswap chains: per-gate, like the reference baseline plan
+        res = subprocess.run([str(CLI), "--file", str(circuit), "-t", "16", "--fuse", f, "--quiet"], cwd=cwd, capture_output=True, text=True)
+        wall = time.perf_counter() - t0
+    if res.returncode != 0:
+        print(json.dumps({"benchmark": name, "error": res.stderr[-300:]}))
+        continue
+    out = res.stdout
+    stats = json.loads(out[out.rindex("{\n  \"statistics\""):])["statistics"]
+    stats["wall_s"] = wall
+    stats["fuse"] = int(f)
+    print(json.dumps(stats), flush=True)
