@@ -5,6 +5,9 @@
 // the C-ABI (include/flatdd_b200.h).  Additions: --gpu D (device), --fuse 3 (GPU cost model),
 // --bin FILE (final state as raw little-endian fp64: real array then imag array), --trace FILE
 // (also record the boundary traffic), --quiet.
+// Multi-GPU: start one process per GPU with --world N --rank r --rendezvous FILE (rank 0 writes the
+// NCCL unique id there, the others wait for it); every rank runs the same driver on the same circuit,
+// holds the shard with top index bits r and writes it to <--bin>.rank<r>.
 #include "cxxopts.hpp"
 #include "nlohmann/json.hpp"
 #include "reference_binding.hpp"
@@ -15,6 +18,7 @@
 #include <iostream>
 #include <memory>
 #include <string>
+#include <thread>
 
 int main(int argc, char** argv) {
     cxxopts::Options options("flatdd_gpu", "FlatDD with a B200 array phase");
@@ -33,6 +37,10 @@ int main(int argc, char** argv) {
         ("gpu", "CUDA device", cxxopts::value<int>()->default_value("0"))
         ("bin", "write the final state as raw fp64 (re[], im[])", cxxopts::value<std::string>())
         ("trace", "record the boundary traffic to this file", cxxopts::value<std::string>())
+        ("world", "number of shards / processes (power of two)", cxxopts::value<int>()->default_value("1"))
+        ("rank", "rank of this process", cxxopts::value<int>()->default_value("0"))
+        ("rendezvous", "file through which rank 0 hands out the NCCL unique id", cxxopts::value<std::string>()->default_value(""))
+        ("exchange", "0 = peer-memory kernel, 1 = NCCL send/recv", cxxopts::value<int>()->default_value("0"))
         ("quiet", "no progress output");
     // clang-format on
     auto vm = options.parse(argc, argv);
@@ -45,9 +53,33 @@ int main(int argc, char** argv) {
     auto circuit = std::make_unique<qc::QuantumComputation>(fname);
     const int nQubits = static_cast<int>(circuit->getNqubits());
 
+    const int world = vm["world"].as<int>();
+    const int rank = vm["rank"].as<int>();
     std::unique_ptr<fddb200::GpuArrayBackend> gpu;
     try {
-        gpu = std::make_unique<fddb200::GpuArrayBackend>(nQubits, vm["gpu"].as<int>());
+        if (world > 1) {
+            const std::string rendezvous = vm["rendezvous"].as<std::string>();
+            if (rendezvous.empty()) throw std::runtime_error("--world needs --rendezvous FILE");
+            char id[128];
+            if (rank == 0) {
+                fddb200::fddCheck(fdd_comm_unique_id(id), "fdd_comm_unique_id");
+                std::ofstream tmp(rendezvous + ".tmp", std::ios::binary);
+                tmp.write(id, sizeof id);
+                tmp.close();
+                std::rename((rendezvous + ".tmp").c_str(), rendezvous.c_str());
+            } else {
+                for (int tries = 0;; ++tries) {
+                    std::ifstream in(rendezvous, std::ios::binary);
+                    if (in.read(id, sizeof id)) break;
+                    if (tries > 6000) throw std::runtime_error("rendezvous file did not appear: " + rendezvous);
+                    std::this_thread::sleep_for(std::chrono::milliseconds(10));
+                }
+            }
+            const int device = vm.count("gpu") > 0 && vm["gpu"].count() > 0 ? vm["gpu"].as<int>() : rank;
+            gpu = std::make_unique<fddb200::GpuArrayBackend>(nQubits, device, rank, world, id, vm["exchange"].as<int>());
+        } else {
+            gpu = std::make_unique<fddb200::GpuArrayBackend>(nQubits, vm["gpu"].as<int>());
+        }
     } catch (const std::exception& e) {
         std::cerr << "flatdd_gpu: " << e.what() << "\n";
         return 3; // no CPU fallback
@@ -67,7 +99,8 @@ int main(int argc, char** argv) {
     sim.fuse = vm["fuse"].as<unsigned int>();
     sim.enable_cache = vm.count("no_cache") == 0;
     sim.ddsim_convert = vm.count("DDSIM_convert") > 0;
-    sim.verbose = vm.count("quiet") == 0;
+    sim.verbose = vm.count("quiet") == 0 && rank == 0;
+    sim.worldSize = world;
 
     sim.simulate();
     const auto t2 = std::chrono::high_resolution_clock::now();
@@ -78,8 +111,9 @@ int main(int argc, char** argv) {
         double* re = nullptr;
         double* im = nullptr;
         sim.getVector(re, im); // converts the DD on the device if the switch never fired
-        const std::size_t dim = std::size_t{1} << sim.getNumberOfQubits();
-        if (vm.count("pv") > 0) {
+        std::size_t dim = std::size_t{1} << sim.getNumberOfQubits();
+        for (int w = world; w > 1; w >>= 1) dim >>= 1; // a shard
+        if (vm.count("pv") > 0 && world == 1) {
             std::ofstream out("../../log/results/state/" + sim.getName() + "_FlatDD.txt");
             if (out.is_open()) {
                 for (std::size_t q = 0; q < dim; ++q) out << re[q] << " " << im[q] << std::endl;
@@ -89,7 +123,7 @@ int main(int argc, char** argv) {
             }
         }
         if (vm.count("bin") > 0) {
-            std::ofstream out(vm["bin"].as<std::string>(), std::ios::binary);
+            std::ofstream out(vm["bin"].as<std::string>() + (world > 1 ? ".rank" + std::to_string(rank) : std::string()), std::ios::binary);
             out.write(reinterpret_cast<const char*>(re), static_cast<std::streamsize>(dim * sizeof(double)));
             out.write(reinterpret_cast<const char*>(im), static_cast<std::streamsize>(dim * sizeof(double)));
         }
@@ -112,7 +146,11 @@ int main(int argc, char** argv) {
                                {"array_phase_time", sim.arrayPhaseTime},
                                {"gate_merging_time", sim.gateMergingTime},
                                {"gates_per_sec_array_phase", sim.arrayPhaseTime > 0 ? static_cast<double>(sim.arrayPhaseOps) / sim.arrayPhaseTime : 0.0},
-                               {"gpu_kernel_launches", fdd_launch_count(gpu->ctx())}};
+                               {"gpu_kernel_launches", fdd_launch_count(gpu->ctx())},
+                               {"world", world},
+                               {"rank", rank},
+                               {"exchanges", sim.exchanges}};
+    if (rank != 0) return 0; // rank 0 reports
     std::ofstream timeFile("../../log/results/time/" + sim.getName() + "_FlatDD.txt");
     if (timeFile.is_open()) {
         for (const auto& t : sim.getTimeRecord1()) timeFile << t << std::endl;

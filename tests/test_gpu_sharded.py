@@ -101,3 +101,30 @@ def test_sharded_reference_circuits(name, golden, tmp_path):
     else:
         idx, sr, si = G.samples(golden, G.TRAVEL)
         assert np.max(np.abs(got[idx.astype(np.int64)] - (sr + 1j * si))) < 1e-10
+
+
+def test_sharded_cli_two_processes(tmp_path):
+    """The C++ host binary itself, one process per GPU: rendezvous through a file, same circuit on
+    both ranks, shards written per rank and compared with the reference's final state."""
+    import subprocess
+    from tests.test_gpu_cli import CLI
+    if n_gpus() < 2 or not CLI.exists():
+        pytest.skip("needs 2 GPUs and build/flatdd_gpu")
+    circuit = ROOT / "tests" / "circuits" / "mix_n12.qasm"
+    cwd = tmp_path / "build" / "apps"
+    cwd.mkdir(parents=True)
+    (tmp_path / "log" / "results" / "time").mkdir(parents=True)
+    (tmp_path / "log" / "results" / "state").mkdir(parents=True)
+    procs = [subprocess.Popen([str(CLI), "--file", str(circuit), "-t", "8", "--fuse", "3", "--quiet", "--world", "2", "--rank", str(r),
+                               "--rendezvous", str(tmp_path / "nccl_id"), "--bin", str(tmp_path / "state.bin")],
+                              cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    shards = []
+    for r in range(2):
+        raw = np.fromfile(str(tmp_path / "state.bin") + f".rank{r}", dtype="<f8")
+        shards.append(raw[: raw.size // 2] + 1j * raw[raw.size // 2:])
+    got = np.concatenate(shards)  # canonical layout: rank = top index bit
+    fr, fi = G.final_state("mix_n12_f1")
+    assert np.max(np.abs(got - (fr + 1j * fi))) < 1e-10
+    assert '"exchanges"' in outs[0][0]
