@@ -42,7 +42,6 @@ if str(ROOT) not in sys.path:
 WORKLOAD = "supremacy_n26"
 METRIC = "array_phase_gates_per_sec"
 UNIT = "gates/s"
-SAMPLE_OPS = 160  # array-phase operations in the CPU sample circuit (oracle/make_golden.py samples)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -201,8 +201,10 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
     const CompiledGate& h = g->host;
     if (h.n != c->n) throw std::invalid_argument("gate has " + std::to_string(h.n) + " qubits, context has " + std::to_string(c->n));
     if (!c->hasState) throw std::logic_error("no state: call fdd_convert / fdd_set_state / fdd_set_zero_state first");
-    if (c->world > 1 && h.topLevel >= c->nLocal && c->peerBuf[0][0] == nullptr) {
-        throw std::logic_error("gate acts on a global qubit but the shards are not connected (fdd_comm_init)");
+    if (c->world > 1 && (h.nonDiagMask >> c->nLocal) != 0) {
+        // reading a peer's buffer while that peer runs its own launch would need cross-rank ordering;
+        // the contract is: swap the global qubit with a local one first (fdd_exchange_qubits)
+        throw std::logic_error("gate is non-diagonal on a global qubit: exchange it with a local qubit first (fdd_exchange_qubits)");
     }
     WalkParams p{};
     p.y = c->buf[c->cur];

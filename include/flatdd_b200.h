@@ -95,7 +95,8 @@ int fdd_destroy(fdd_ctx* ctx);
 int fdd_n_qubits(const fdd_ctx* ctx);
 int fdd_n_local_qubits(const fdd_ctx* ctx);
 int fdd_synchronize(fdd_ctx* ctx);
-/* Tunables for experiments ("dmavm_variant", "warps_per_cta", "ctas_per_sm", "prefetch", "exact_convert"). */
+/* Tunables for experiments: "dmavm_variant" (2 tile kernel where the gate allows, 1 / 0 walk kernels, 9 chunk kernel),
+ * "warps_per_cta", "ctas_per_sm", "prefetch", "tile_mode", "dense_slots", "exchange_unroll", "exchange_ctas_per_sm". */
 int fdd_set_option(fdd_ctx* ctx, const char* key, long value);
 
 /* ---- multi-GPU (one process per GPU) ----------------------------------
@@ -141,7 +142,9 @@ int fdd_apply(fdd_ctx* ctx, const fdd_matdd* gate);
 int fdd_gate_compile(fdd_ctx* ctx, const fdd_matdd* gate, fdd_gate** out);
 int fdd_gate_apply(fdd_ctx* ctx, const fdd_gate* gate);
 int fdd_gate_free(fdd_gate* gate);
-/* Facts about a compiled gate: key in {"kind","max_paths","max_sub_k","upper_nodes","sub_tables","nnz_per_row_max","global_levels"}. */
+/* Facts about a compiled gate: key in {"kind", "max_paths", "max_sub_k", "upper_nodes", "upper_depth", "sub_tables",
+ * "nnz_per_row_max", "nnz", "top_level", "stack_cap", "tileable", "uniform", "sub_tile_bits", "non_diag_upper",
+ * "non_diag_mask", "tile_mask", "fill_mask"}; -1 for an unknown key. */
 long fdd_gate_info(const fdd_gate* gate, const char* key);
 
 /* Literal drop-in for one DDArrMultiplyIP call on HOST arrays (SoA re/im, nDim = 2^n):
