@@ -239,15 +239,18 @@ def gpu_arm(args) -> int:
         dist.broadcast_object_list(uid, src=0, device=device)
         ctx.comm_init(uid[0])
     stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
-    steps = []  # ("g", compiled) | ("x", global bit, local bit) | ("r", a, b)
+    steps = []  # ("g", [compiled gates of one schedule segment]) | ("x", global bit, local bit) | ("r", a, b)
     for r in records[1:]:
         if r.kind == 2:
-            steps.append(("g", ctx.compile(r.dd)))
+            if steps and steps[-1][0] == "g":
+                steps[-1][1].append(ctx.compile(r.dd))
+            else:
+                steps.append(("g", [ctx.compile(r.dd)]))
         elif r.kind == 3:
             steps.append(("x",) + tuple(r.exchange))
         elif r.kind == 4:
             steps.append(("r",) + tuple(r.exchange))
-    n_gates = sum(1 for s in steps if s[0] == "g")
+    n_gates = sum(len(s[1]) for s in steps if s[0] == "g")
     n_exch = sum(1 for s in steps if s[0] == "x")
     method = args.exchange_method
 
@@ -262,7 +265,7 @@ def gpu_arm(args) -> int:
         ctx.convert(vec)
         for s in steps:
             if s[0] == "g":
-                ctx.apply_compiled(s[1])
+                ctx.apply_compiled_many(s[1])
             elif s[0] == "x":
                 if exchange_events is not None:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -293,7 +296,7 @@ def gpu_arm(args) -> int:
         ev[3 * s + 1].record(stream)
         for st in steps:
             if st[0] == "g":
-                ctx.apply_compiled(st[1])
+                ctx.apply_compiled_many(st[1])
             elif st[0] == "x":
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)

@@ -28,7 +28,7 @@ EXPORTS = [
     "fdd_version", "fdd_last_error", "fdd_device_count", "fdd_create", "fdd_create_sharded", "fdd_destroy",
     "fdd_n_qubits", "fdd_n_local_qubits", "fdd_synchronize", "fdd_set_option", "fdd_comm_unique_id", "fdd_comm_init",
     "fdd_exchange_qubits", "fdd_relabel_qubits", "fdd_barrier",
-    "fdd_convert", "fdd_apply", "fdd_gate_compile", "fdd_gate_apply", "fdd_gate_free", "fdd_gate_info",
+    "fdd_convert", "fdd_apply", "fdd_gate_compile", "fdd_gate_apply", "fdd_gate_apply_many", "fdd_gate_free", "fdd_gate_info",
     "fdd_ddarr_multiply", "fdd_mac_count", "fdd_cost_ip", "fdd_cost_op1", "fdd_cost_gpu", "fdd_matdd_info", "fdd_get_state",
     "fdd_set_state", "fdd_set_zero_state", "fdd_get_amplitudes", "fdd_norm2", "fdd_state_device_ptr",
     "fdd_get_permutation", "fdd_canonicalize", "fdd_last_kernel_ms", "fdd_set_timing", "fdd_launch_count", "fdd_stream",
@@ -66,6 +66,7 @@ class Library:
         L.fdd_apply.argtypes = [vp, ddp]
         L.fdd_gate_compile.argtypes = [vp, ddp, ctypes.POINTER(vp)]
         L.fdd_gate_apply.argtypes = [vp, vp]
+        L.fdd_gate_apply_many.argtypes = [vp, ctypes.POINTER(vp), i32]
         L.fdd_gate_free.argtypes = [vp]
         L.fdd_gate_info.argtypes = [vp, ctypes.c_char_p]
         L.fdd_gate_info.restype = ctypes.c_long
@@ -253,6 +254,11 @@ class Context:
 
     def apply_compiled(self, gate: CompiledGate):
         self.L.check(self.L.lib.fdd_gate_apply(self._h, gate._h))
+
+    def apply_compiled_many(self, gates):
+        """One C call for a run of compiled gates (a schedule segment between two exchanges)."""
+        arr = (ctypes.c_void_p * len(gates))(*[g._h for g in gates])
+        self.L.check(self.L.lib.fdd_gate_apply_many(self._h, arr, len(gates)))
 
     def set_zero_state(self):
         self.L.check(self.L.lib.fdd_set_zero_state(self._h))

@@ -177,7 +177,9 @@ using Kernel = void (*)(const WalkParams);
 template <int TB> Kernel tileKernelTB(int mode, int kt) {
     switch (mode) {
         case 0: return dmavm_tile_kernel<TB, 0, 0>;
-        case 1: return kt == 2 ? dmavm_tile_kernel<TB, 1, 2> : (kt == 4 ? dmavm_tile_kernel<TB, 1, 4> : dmavm_tile_kernel<TB, 1, 8>);
+        case 1:
+            return kt == 2 ? dmavm_tile_kernel<TB, 1, 2>
+                           : (kt == 4 ? dmavm_tile_kernel<TB, 1, 4> : (kt == 8 ? dmavm_tile_kernel<TB, 1, 8> : dmavm_tile_kernel<TB, 1, 16>));
         case 2: return kt == 2 ? dmavm_tile_kernel<TB, 2, 2> : (kt == 4 ? dmavm_tile_kernel<TB, 2, 4> : dmavm_tile_kernel<TB, 2, 8>);
         case 4: return kt == 2 ? dmavm_tile_kernel<TB, 4, 2> : (kt == 4 ? dmavm_tile_kernel<TB, 4, 4> : dmavm_tile_kernel<TB, 4, 8>);
         default:
@@ -242,10 +244,13 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
         bool allIdentity = true;
         for (uint8_t f : h.subFlags) allIdentity = allIdentity && (f & SUB_IDENTITY);
         // ELL width rounded up for static unrolling; wider tables take the run-time loop of MODE 3
-        const int kt = h.kMax <= 2 ? 2 : (h.kMax <= 4 ? 4 : (h.kMax <= 8 ? 8 : 0));
+        int kt = h.kMax <= 2 ? 2 : (h.kMax <= 4 ? 4 : (h.kMax <= 8 ? 8 : 0));
         int mode = 0;
         if (!allIdentity) {
-            if (h.nSub == 1 && kt > 0) {
+            if (h.nSub == 1 && h.kMax == 16 && h.maxPaths <= 2) {
+                kt = 16; // a block that is dense on four of the five lane qubits: gather first, table in registers
+                mode = 1;
+            } else if (h.nSub == 1 && kt > 0) {
                 // instruction estimates per output segment: gather first P(8+5K), shuffle last 9P+8K
                 mode = h.maxPaths * (8 + 5 * kt) <= 9 * h.maxPaths + 8 * kt ? 1 : 2;
             } else {
@@ -737,6 +742,17 @@ int fdd_gate_apply(fdd_ctx* ctx, const fdd_gate* gate) {
         if (ctx == nullptr || gate == nullptr) throw std::invalid_argument("null argument");
         useDevice(ctx);
         launchWalk(ctx, gate);
+    });
+}
+
+int fdd_gate_apply_many(fdd_ctx* ctx, const fdd_gate* const* gates, int count) {
+    return guarded([&] {
+        if (ctx == nullptr || (gates == nullptr && count > 0)) throw std::invalid_argument("null argument");
+        useDevice(ctx);
+        for (int i = 0; i < count; ++i) {
+            if (gates[i] == nullptr) throw std::invalid_argument("null gate in the list");
+            launchWalk(ctx, gates[i]);
+        }
     });
 }
 

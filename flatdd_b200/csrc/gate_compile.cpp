@@ -299,8 +299,8 @@ CompiledGate compileGate(const fdd_matdd& g, int nLocal) {
         out.kMax = std::max(out.kMax, k);
     }
     out.kTrue = out.kMax;
-    // pad the ELL width to 2, 4 or 8 so the kernels can unroll it without a bound check
-    if (out.kMax <= 8) out.kMax = out.kMax <= 2 ? 2 : (out.kMax <= 4 ? 4 : 8);
+    // pad the ELL width to 2, 4, 8 or 16 so the kernels can unroll it without a bound check
+    if (out.kMax <= 16) out.kMax = out.kMax <= 2 ? 2 : (out.kMax <= 4 ? 4 : (out.kMax <= 8 ? 8 : 16));
     out.subCol.assign(static_cast<std::size_t>(out.nSub) * out.kMax * 32, 0);
     out.subW.assign(static_cast<std::size_t>(out.nSub) * out.kMax * 32 * 2, 0.0);
     out.subFlags.assign(static_cast<std::size_t>(out.nSub), 0);

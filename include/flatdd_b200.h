@@ -141,6 +141,8 @@ int fdd_apply(fdd_ctx* ctx, const fdd_matdd* gate);
 /* Same in two steps, so a schedule can be compiled once and replayed. */
 int fdd_gate_compile(fdd_ctx* ctx, const fdd_matdd* gate, fdd_gate** out);
 int fdd_gate_apply(fdd_ctx* ctx, const fdd_gate* gate);
+/* Applies `count` compiled gates back to back (one call per schedule segment instead of one per gate). */
+int fdd_gate_apply_many(fdd_ctx* ctx, const fdd_gate* const* gates, int count);
 int fdd_gate_free(fdd_gate* gate);
 /* Facts about a compiled gate: key in {"kind", "max_paths", "max_sub_k", "upper_nodes", "upper_depth", "sub_tables",
  * "nnz_per_row_max", "nnz", "top_level", "stack_cap", "tileable", "uniform", "sub_tile_bits", "non_diag_upper",
