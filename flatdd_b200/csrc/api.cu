@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -310,6 +311,10 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
                 }
             }
             c->launchShapes.emplace(key, std::make_pair(bestW, bestC));
+            if (std::getenv("FLATDD_B200_DEBUG") != nullptr) {
+                std::fprintf(stderr, "[flatdd_b200] tile kernel TB=%d mode=%d kt=%d: %d warps/CTA x %d CTAs/SM, smem %zu B (cta %zu + %zu per warp), paths %d, uniform %d, dense %d\n",
+                             h.subTileBits, mode, kt, bestW, bestC, fixedT + bestW * perWarpT, fixedT, perWarpT, p.maxPaths, p.uniform, p.denseSlots);
+            }
         }
         if (bestW > 0) {
             const size_t smemT = fixedT + static_cast<size_t>(bestW) * perWarpT;
