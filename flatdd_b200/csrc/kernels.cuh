@@ -137,30 +137,44 @@ __global__ void __launch_bounds__(256) convert_kernel(const ConvertParams p) {
             }
         }
         // ---- phase B: sweep the segments, lane = amplitude -------------------------------------
+        // four segments at a time: four independent multiply chains per lane hide the latency of the
+        // dependent table look-ups (the arithmetic of every chain is unchanged)
         const int nSegTile = min(32u, p.nSeg - tile * 32u);
-        for (int j = 0; j < nSegTile; ++j) {
-            const int nodeJ = __shfl_sync(0xffffffffu, node, j);
-            const double2 cJ = shfl2(c, j);
-            const bool deadJ = __shfl_sync(0xffffffffu, static_cast<int>(dead), j) != 0;
+        constexpr int U = 4;
+        for (int j0 = 0; j0 < nSegTile; j0 += U) {
+            double2 a[U];
+            int u[U];
+            bool z[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const int j = min(j0 + k, nSegTile - 1);
+                u[k] = __shfl_sync(0xffffffffu, node, j);
+                a[k] = shfl2(c, j);
+                z[k] = __shfl_sync(0xffffffffu, static_cast<int>(dead), j) != 0;
+            }
             if (lane < segLen) {
-                double2 a = cJ;
-                bool z = deadJ;
-                int u = nodeJ;
-                if (!z) {
-                    for (int lv = S - 1; lv >= 0; --lv) {
-                        const VecNode& nd = nodes[u];
-                        const int b = (lane >> lv) & 1;
-                        const double2 w = nd.w[b];
-                        a = cmul_exact(a, w);
-                        if (w.x == 0.0 && w.y == 0.0) {
-                            z = true;
-                            break;
+                for (int lv = S - 1; lv >= 0; --lv) {
+                    const int b = (lane >> lv) & 1;
+#pragma unroll
+                    for (int k = 0; k < U; ++k) {
+                        if (!z[k]) {
+                            const VecNode& nd = nodes[u[k]];
+                            const double2 w = nd.w[b];
+                            a[k] = cmul_exact(a[k], w);
+                            if (w.x == 0.0 && w.y == 0.0) {
+                                z[k] = true;
+                            } else {
+                                u[k] = nd.child[b];
+                            }
                         }
-                        u = nd.child[b];
                     }
                 }
-                if (z) a = make_double2(0.0, 0.0);
-                st_stream(p.out + ((static_cast<uint64_t>(tile) * 32u + j) << S) + lane, a);
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    if (j0 + k < nSegTile) {
+                        st_stream(p.out + ((static_cast<uint64_t>(tile) * 32u + j0 + k) << S) + lane, z[k] ? make_double2(0.0, 0.0) : a[k]);
+                    }
+                }
             }
         }
     }
