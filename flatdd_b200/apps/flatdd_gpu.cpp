@@ -41,6 +41,7 @@ int main(int argc, char** argv) {
         ("rank", "rank of this process", cxxopts::value<int>()->default_value("0"))
         ("rendezvous", "file through which rank 0 hands out the NCCL unique id", cxxopts::value<std::string>()->default_value(""))
         ("exchange", "0 = peer-memory kernel, 1 = NCCL send/recv", cxxopts::value<int>()->default_value("0"))
+        ("time-gates", "time every DMAVM launch with CUDA events (synchronises per launch) and report achieved HBM GB/s")
         ("quiet", "no progress output");
     // clang-format on
     auto vm = options.parse(argc, argv);
@@ -92,6 +93,7 @@ int main(int argc, char** argv) {
         tee = std::make_unique<fddb200::TeeBackend>(std::vector<fddb200::ArrayBackend*>{gpu.get(), recorder.get()});
         backend = tee.get();
     }
+    if (vm.count("time-gates") > 0) gpu->setTiming(true);
     fddb200::RefGpuSwitchSimulator sim(std::move(circuit), backend);
     sim.threshold = vm["thresh"].as<double>();
     const auto nThread = vm["t"].as<unsigned int>();
@@ -147,6 +149,8 @@ int main(int argc, char** argv) {
                                {"gate_merging_time", sim.gateMergingTime},
                                {"gates_per_sec_array_phase", sim.arrayPhaseTime > 0 ? static_cast<double>(sim.arrayPhaseOps) / sim.arrayPhaseTime : 0.0},
                                {"gpu_kernel_launches", fdd_launch_count(gpu->ctx())},
+                               {"dmavm_kernel_ms_total", sim.kernelMsTotal},
+                               {"dmavm_hbm_gbs", sim.kernelMsTotal > 0 ? 32.0 * std::ldexp(1.0, nQubits) / (world > 1 ? world : 1) * static_cast<double>(sim.launches) / (sim.kernelMsTotal * 1e-3) / 1e9 : 0.0},
                                {"world", world},
                                {"rank", rank},
                                {"exchanges", sim.exchanges}};

@@ -39,6 +39,8 @@ public:
     virtual void exchange(int /*globalPhysicalBit*/, int /*localPhysicalBit*/) {
         throw std::runtime_error("this backend holds an unsharded state");
     }
+    // device milliseconds of the last convert / apply when per-launch timing is on (0 otherwise)
+    virtual double lastKernelMs() { return 0.0; }
     // the logical qubits at two physical bits trade names (absorbed SWAP gate); no data moves
     virtual void relabel(int /*physicalBitA*/, int /*physicalBitB*/) {}
     virtual void canonicalize() {}
@@ -84,6 +86,12 @@ public:
     }
     void relabel(int a, int b) override { fddCheck(fdd_relabel_qubits(ctx_, a, b), "fdd_relabel_qubits"); }
     void canonicalize() override { fddCheck(fdd_canonicalize(ctx_), "fdd_canonicalize"); }
+    void setTiming(bool on) { fddCheck(fdd_set_timing(ctx_, on ? 1 : 0), "fdd_set_timing"); }
+    double lastKernelMs() override {
+        float ms = 0.0F;
+        fddCheck(fdd_last_kernel_ms(ctx_, &ms), "fdd_last_kernel_ms");
+        return static_cast<double>(ms);
+    }
     [[nodiscard]] fdd_ctx* ctx() const { return ctx_; }
 
 private:

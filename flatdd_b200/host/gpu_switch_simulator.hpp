@@ -148,6 +148,7 @@ public:
     std::size_t launches = 0;      // DMAVM launches issued
     double gateMergingTime = 0.0;
     double arrayPhaseTime = 0.0;
+    double kernelMsTotal = 0.0;    // sum of device times of the DMAVM launches (needs per-launch timing on the backend)
     bool verbose = true;
 
 private:
@@ -288,6 +289,7 @@ private:
     void launch(const MEdge& gate, int nOriginal) {
         const auto flat = flatten<4, MEdge, WeightTraits>(gate, nq());
         backend->apply(flat, nOriginal);
+        kernelMsTotal += backend->lastKernelMs();
         ++launches;
         arrayPhaseOps += static_cast<std::size_t>(nOriginal);
         hostValid = false;
