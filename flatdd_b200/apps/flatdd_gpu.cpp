@@ -15,7 +15,9 @@
 #include <chrono>
 #include <cmath>
 #include <fstream>
+#include <algorithm>
 #include <iostream>
+#include <map>
 #include <memory>
 #include <string>
 #include <thread>
@@ -41,6 +43,8 @@ int main(int argc, char** argv) {
         ("rank", "rank of this process", cxxopts::value<int>()->default_value("0"))
         ("rendezvous", "file through which rank 0 hands out the NCCL unique id", cxxopts::value<std::string>()->default_value(""))
         ("exchange", "0 = peer-memory kernel, 1 = NCCL send/recv", cxxopts::value<int>()->default_value("0"))
+        ("shots", "sample this many measurement outcomes of all qubits on the device (the reference skips measurements)", cxxopts::value<unsigned long>()->default_value("0"))
+        ("seed", "seed of the sampler", cxxopts::value<unsigned long>()->default_value("0"))
         ("time-gates", "time every DMAVM launch with CUDA events (synchronises per launch) and report achieved HBM GB/s")
         ("quiet", "no progress output");
     // clang-format on
@@ -132,6 +136,29 @@ int main(int argc, char** argv) {
     }
     if (recorder) recorder->close();
 
+    // measurement sampling on the device: most frequent outcomes as {bitstring: count}
+    nlohmann::json sampled;
+    const auto shots = vm["shots"].as<unsigned long>();
+    if (shots > 0 && world == 1) {
+        double* re = nullptr;
+        double* im = nullptr;
+        if (!sim.switched) sim.getVector(re, im); // make sure the state is on the device
+        std::vector<uint64_t> outcomes(shots);
+        fddb200::fddCheck(fdd_sample(gpu->ctx(), shots, vm["seed"].as<unsigned long>(), outcomes.data()), "fdd_sample");
+        std::map<uint64_t, std::size_t> histogram;
+        for (uint64_t o : outcomes) ++histogram[o];
+        std::vector<std::pair<std::size_t, uint64_t>> byCount;
+        for (const auto& kv : histogram) byCount.emplace_back(kv.second, kv.first);
+        std::sort(byCount.rbegin(), byCount.rend());
+        for (std::size_t k = 0; k < byCount.size() && k < 16; ++k) {
+            std::string bits(static_cast<std::size_t>(nQubits), '0');
+            for (int q = 0; q < nQubits; ++q) {
+                if ((byCount[k].second >> q) & 1U) bits[static_cast<std::size_t>(nQubits - 1 - q)] = '1';
+            }
+            sampled[bits] = byCount[k].first;
+        }
+    }
+
     nlohmann::json outputObj;
     outputObj["statistics"] = {{"simulation_time", durationSimulation.count()},
                                {"benchmark", sim.getName()},
@@ -154,6 +181,7 @@ int main(int argc, char** argv) {
                                {"world", world},
                                {"rank", rank},
                                {"exchanges", sim.exchanges}};
+    if (!sampled.empty()) outputObj["samples_top16"] = sampled;
     if (rank != 0) return 0; // rank 0 reports
     std::ofstream timeFile("../../log/results/time/" + sim.getName() + "_FlatDD.txt");
     if (timeFile.is_open()) {

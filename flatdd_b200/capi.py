@@ -30,7 +30,7 @@ EXPORTS = [
     "fdd_exchange_qubits", "fdd_relabel_qubits", "fdd_barrier",
     "fdd_convert", "fdd_apply", "fdd_gate_compile", "fdd_gate_apply", "fdd_gate_apply_many", "fdd_gate_free", "fdd_gate_info",
     "fdd_ddarr_multiply", "fdd_mac_count", "fdd_cost_ip", "fdd_cost_op1", "fdd_cost_gpu", "fdd_matdd_info", "fdd_get_state",
-    "fdd_set_state", "fdd_set_zero_state", "fdd_get_amplitudes", "fdd_norm2", "fdd_state_device_ptr",
+    "fdd_set_state", "fdd_set_zero_state", "fdd_get_amplitudes", "fdd_norm2", "fdd_sample", "fdd_state_device_ptr",
     "fdd_get_permutation", "fdd_canonicalize", "fdd_last_kernel_ms", "fdd_set_timing", "fdd_launch_count", "fdd_stream",
 ]
 
@@ -81,6 +81,7 @@ class Library:
         L.fdd_set_zero_state.argtypes = [vp]
         L.fdd_get_amplitudes.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint64, dp]
         L.fdd_norm2.argtypes = [vp, dp]
+        L.fdd_sample.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]
         L.fdd_state_device_ptr.argtypes = [vp, ctypes.POINTER(vp)]
         L.fdd_get_permutation.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
         L.fdd_canonicalize.argtypes = [vp]
@@ -292,6 +293,12 @@ class Context:
         out = ctypes.c_double(0)
         self.L.check(self.L.lib.fdd_norm2(self._h, ctypes.byref(out)))
         return out.value
+
+    def sample(self, n_shots: int, seed: int = 0) -> np.ndarray:
+        """Local physical indices of n_shots basis states drawn with probability |amp|^2 / shard norm."""
+        out = np.zeros(n_shots, dtype=np.uint64)
+        self.L.check(self.L.lib.fdd_sample(self._h, n_shots, seed, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))))
+        return out
 
     def set_timing(self, enabled: bool):
         self.L.check(self.L.lib.fdd_set_timing(self._h, 1 if enabled else 0))

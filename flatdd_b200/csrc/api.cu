@@ -935,6 +935,65 @@ int fdd_norm2(fdd_ctx* ctx, double* out) {
     });
 }
 
+int fdd_sample(fdd_ctx* ctx, uint64_t n_shots, uint64_t seed, uint64_t* local_indices) {
+    return guarded([&] {
+        if (ctx == nullptr || (local_indices == nullptr && n_shots > 0)) throw std::invalid_argument("null argument");
+        if (!ctx->hasState) throw std::logic_error("no state");
+        if (n_shots == 0) return;
+        useDevice(ctx);
+        const uint64_t dim = ctx->localDim();
+        const uint32_t blockAmps = static_cast<uint32_t>(std::min<uint64_t>(dim, 4096));
+        const uint32_t nBlocks = static_cast<uint32_t>((dim + blockAmps - 1) / blockAmps);
+        double* dMass = nullptr;
+        CUDA_TRY(cudaMallocAsync(&dMass, sizeof(double) * nBlocks, ctx->stream));
+        block_mass_kernel<<<nBlocks, 256, 0, ctx->stream>>>(ctx->buf[ctx->cur], dim, blockAmps, dMass);
+        CUDA_TRY(cudaGetLastError());
+        std::vector<double> mass(nBlocks);
+        CUDA_TRY(cudaMemcpyAsync(mass.data(), dMass, sizeof(double) * nBlocks, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaFreeAsync(dMass, ctx->stream));
+        std::vector<double> prefix(nBlocks + 1, 0.0);
+        for (uint32_t b = 0; b < nBlocks; ++b) prefix[b + 1] = prefix[b] + mass[b];
+        const double total = prefix[nBlocks];
+        if (!(total > 0.0)) throw std::logic_error("the state has zero norm");
+        // splitmix64: deterministic, seedable, good enough for shot sampling
+        uint64_t x = seed;
+        auto next = [&x]() {
+            uint64_t z = (x += 0x9e3779b97f4a7c15ULL);
+            z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+            z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+            return z ^ (z >> 31);
+        };
+        std::vector<uint32_t> shotBlock(n_shots);
+        std::vector<double> shotResidual(n_shots);
+        for (uint64_t sIdx = 0; sIdx < n_shots; ++sIdx) {
+            const double u = static_cast<double>(next() >> 11) * (1.0 / 9007199254740992.0) * total;
+            uint32_t b = static_cast<uint32_t>(std::upper_bound(prefix.begin() + 1, prefix.end(), u) - (prefix.begin() + 1));
+            if (b >= nBlocks) b = nBlocks - 1;
+            while (b > 0 && mass[b] == 0.0) --b; // never land in an empty block
+            shotBlock[sIdx] = b;
+            shotResidual[sIdx] = u - prefix[b];
+        }
+        uint32_t* dBlock = nullptr;
+        double* dRes = nullptr;
+        uint64_t* dOut = nullptr;
+        CUDA_TRY(cudaMallocAsync(&dBlock, sizeof(uint32_t) * n_shots, ctx->stream));
+        CUDA_TRY(cudaMallocAsync(&dRes, sizeof(double) * n_shots, ctx->stream));
+        CUDA_TRY(cudaMallocAsync(&dOut, sizeof(uint64_t) * n_shots, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(dBlock, shotBlock.data(), sizeof(uint32_t) * n_shots, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(dRes, shotResidual.data(), sizeof(double) * n_shots, cudaMemcpyHostToDevice, ctx->stream));
+        const uint64_t threads = n_shots * 32;
+        sample_resolve_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->buf[ctx->cur], dim, blockAmps, dBlock, dRes, n_shots, dOut);
+        CUDA_TRY(cudaGetLastError());
+        ctx->launches += 2;
+        CUDA_TRY(cudaMemcpyAsync(local_indices, dOut, sizeof(uint64_t) * n_shots, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaFreeAsync(dBlock, ctx->stream));
+        CUDA_TRY(cudaFreeAsync(dRes, ctx->stream));
+        CUDA_TRY(cudaFreeAsync(dOut, ctx->stream));
+    });
+}
+
 int fdd_state_device_ptr(fdd_ctx* ctx, void** ptr) {
     if (ctx == nullptr || ptr == nullptr) return fail(FDD_ERR_INVALID, "null argument");
     *ptr = ctx->buf[ctx->cur];

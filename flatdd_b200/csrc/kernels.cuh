@@ -1015,6 +1015,59 @@ __global__ void zero_state_kernel(double2* out, uint64_t n, int setOne) {
         out[i] = make_double2((i == 0 && setOne) ? 1.0 : 0.0, 0.0);
     }
 }
+// ---- measurement sampling ---------------------------------------------------------------------------
+// probability mass of every block of `blockAmps` consecutive amplitudes (one CTA per block, fixed order)
+__global__ void __launch_bounds__(256) block_mass_kernel(const double2* __restrict__ in, uint64_t n, uint32_t blockAmps, double* __restrict__ mass) {
+    __shared__ double sh[8];
+    const uint64_t first = static_cast<uint64_t>(blockIdx.x) * blockAmps;
+    double s = 0.0;
+    for (uint32_t i = threadIdx.x; i < blockAmps && first + i < n; i += blockDim.x) {
+        const double2 v = in[first + i];
+        s = fma(v.x, v.x, s);
+        s = fma(v.y, v.y, s);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) t += sh[w];
+        mass[blockIdx.x] = t;
+    }
+}
+// one warp per shot: walk the chosen block until the running mass passes the shot's residual
+__global__ void __launch_bounds__(256) sample_resolve_kernel(const double2* __restrict__ in, uint64_t n, uint32_t blockAmps,
+                                                             const uint32_t* __restrict__ shotBlock, const double* __restrict__ shotResidual,
+                                                             uint64_t nShots, uint64_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t shot = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (shot >= nShots) return;
+    const uint64_t first = static_cast<uint64_t>(shotBlock[shot]) * blockAmps;
+    const double target = shotResidual[shot];
+    double running = 0.0;
+    uint64_t lastNonZero = first;
+    uint64_t found = ~uint64_t{0};
+    for (uint32_t base = 0; base < blockAmps && found == ~uint64_t{0}; base += 32) {
+        const uint64_t idx = first + base + lane;
+        double pr = 0.0;
+        if (idx < n) {
+            const double2 v = in[idx];
+            pr = fma(v.x, v.x, v.y * v.y);
+        }
+        double incl = pr; // inclusive warp scan
+        for (int o = 1; o < 32; o <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, pr > 0.0 && running + incl > target);
+        const unsigned nz = __ballot_sync(0xffffffffu, pr > 0.0);
+        if (nz != 0) lastNonZero = first + base + (31 - __clz(nz));
+        if (hit != 0) found = first + base + (__ffs(hit) - 1);
+        running += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) out[shot] = found != ~uint64_t{0} ? found : lastNonZero; // rounding at the block end: last populated state
+}
+
 // sum |amp|^2: per-block partial sums in fixed order, final pass on one block (deterministic)
 __global__ void norm2_partial_kernel(const double2* __restrict__ in, uint64_t n, double* __restrict__ partial) {
     __shared__ double sh[32];

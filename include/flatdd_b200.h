@@ -181,6 +181,12 @@ int fdd_set_zero_state(fdd_ctx* ctx);
 int fdd_get_amplitudes(fdd_ctx* ctx, uint64_t first, uint64_t count, double* interleaved);
 /* sum |amp|^2 over the local shard, computed on the device. */
 int fdd_norm2(fdd_ctx* ctx, double* out);
+/* Measurement sampling on the device (the reference skips measurements,
+ * src/SwitchSimulator.cpp:108-113, so there is no parity target): draws `n_shots` basis states of the local shard
+ * with probability |amplitude|^2 / (shard norm) and writes their LOCAL PHYSICAL indices.  Deterministic in `seed`.
+ * Sharded states: draw the rank of every shot from the shard norms (fdd_norm2) first, and map physical to logical
+ * bits with fdd_get_permutation. */
+int fdd_sample(fdd_ctx* ctx, uint64_t n_shots, uint64_t seed, uint64_t* local_indices);
 /* Device pointer of the current state (interleaved complex<double>), for zero-copy hosts. */
 int fdd_state_device_ptr(fdd_ctx* ctx, void** ptr);
 /* Sharded contexts: logical->physical qubit map (length n_qubits) and its undo. */

@@ -53,3 +53,14 @@ def test_cli_final_state_matches_reference(name, threads, fuse, golden):
             assert stats["switched_at_op"] == m["trace"]["switched_at_op"]
     assert any(line.startswith("Switch Overhead:") for line in time_lines)
     assert "Simulation finished" in out
+
+
+@pytest.mark.skipif(not CLI.exists(), reason="build/flatdd_gpu not built (needs the reference checkout)")
+def test_cli_shots_and_time_gates():
+    """--shots samples on the device (GHZ: only 000000 and 111111), --time-gates reports kernel time."""
+    out, stats, re, im, _ = run_cli(ROOT / "tests" / "circuits" / "ghz_n6.qasm", 4, 0, extra=("--shots", "2000", "--seed", "3"))
+    full = json.loads(out[out.rindex("{\n  \"statistics\""):])
+    assert set(full["samples_top16"].keys()) == {"000000", "111111"}
+    assert sum(full["samples_top16"].values()) == 2000
+    out, stats, re, im, _ = run_cli(ROOT / "tests" / "circuits" / "mix_n12.qasm", 8, 3, extra=("--time-gates", "--quiet"))
+    assert stats["dmavm_kernel_ms_total"] > 0 and stats["dmavm_hbm_gbs"] > 0

@@ -268,3 +268,33 @@ def test_full_size_properties(n):
                 got = ctx.get_amplitudes(int(i), 64)
                 want = yr[i:i + 64] + 1j * yi[i:i + 64]
                 assert np.max(np.abs(got - want)) < 1e-13
+
+
+def test_sampling_follows_the_born_rule():
+    """fdd_sample: deterministic in the seed, only populated states, frequencies ~ |amp|^2."""
+    n = 14
+    rng = np.random.default_rng(5)
+    re = np.zeros(1 << n)
+    im = np.zeros(1 << n)
+    support = rng.choice(1 << n, size=37, replace=False)
+    amp = rng.normal(size=37) + 1j * rng.normal(size=37)
+    amp /= np.linalg.norm(amp)
+    re[support], im[support] = amp.real, amp.imag
+    with Context(n) as ctx:
+        ctx.set_state(re, im)
+        shots = ctx.sample(200000, seed=11)
+        again = ctx.sample(200000, seed=11)
+        other = ctx.sample(1000, seed=12)
+    assert np.array_equal(shots, again) and not np.array_equal(shots[:1000], other)
+    assert set(np.unique(shots)) <= set(support.tolist())
+    counts = np.array([(shots == s).sum() for s in support]) / shots.size
+    assert np.max(np.abs(counts - np.abs(amp) ** 2)) < 0.01
+    # a GHZ-like state gives the two extreme outcomes only
+    re[:] = 0.0
+    im[:] = 0.0
+    re[0] = re[-1] = np.sqrt(0.5)
+    with Context(n) as ctx:
+        ctx.set_state(re, im)
+        shots = ctx.sample(4096, seed=1)
+    assert set(np.unique(shots)) == {0, (1 << n) - 1}
+    assert abs((shots == 0).mean() - 0.5) < 0.05
