@@ -26,7 +26,7 @@ class FlatDDError(RuntimeError):
 
 EXPORTS = [
     "fdd_version", "fdd_last_error", "fdd_device_count", "fdd_create", "fdd_create_sharded", "fdd_destroy",
-    "fdd_n_qubits", "fdd_n_local_qubits", "fdd_synchronize", "fdd_set_option", "fdd_comm_unique_id", "fdd_comm_init",
+    "fdd_n_qubits", "fdd_n_local_qubits", "fdd_synchronize", "fdd_set_option", "fdd_get_option", "fdd_comm_unique_id", "fdd_comm_init",
     "fdd_exchange_qubits", "fdd_relabel_qubits", "fdd_barrier",
     "fdd_convert", "fdd_apply", "fdd_gate_compile", "fdd_gate_apply", "fdd_gate_apply_many", "fdd_gate_free", "fdd_gate_info",
     "fdd_ddarr_multiply", "fdd_mac_count", "fdd_cost_ip", "fdd_cost_op1", "fdd_cost_gpu", "fdd_matdd_info", "fdd_get_state",
@@ -57,6 +57,7 @@ class Library:
         L.fdd_n_local_qubits.argtypes = [vp]
         L.fdd_synchronize.argtypes = [vp]
         L.fdd_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_long]
+        L.fdd_get_option.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_long)]
         L.fdd_comm_unique_id.argtypes = [vp]
         L.fdd_comm_init.argtypes = [vp, vp]
         L.fdd_exchange_qubits.argtypes = [vp, i32, i32, i32]
@@ -235,6 +236,11 @@ class Context:
 
     def set_option(self, key: str, value: int):
         self.L.check(self.L.lib.fdd_set_option(self._h, key.encode(), int(value)))
+
+    def get_option(self, key: str) -> int:
+        v = ctypes.c_long(0)
+        self.L.check(self.L.lib.fdd_get_option(self._h, key.encode(), ctypes.byref(v)))
+        return int(v.value)
 
     def synchronize(self):
         self.L.check(self.L.lib.fdd_synchronize(self._h))

@@ -96,6 +96,7 @@ struct fdd_ctx {
     bool timing = false;
     float lastMs = 0.0f;
     uint64_t launches = 0;
+    uint64_t tensorCoreLaunches = 0;
     int smCount = 148;
     // tunables
     int variant = 2;      // 2: tile kernel when the gate allows it, else 1; 1: cp.async ring walk; 0: register walk
@@ -104,6 +105,7 @@ struct fdd_ctx {
     int prefetch = 8;
     int forceMode = -1;   // experiments: force the tile-kernel MODE (1, 2 or 3) where it applies
     int denseSlots = 1;   // experiments: 0 disables the dense register path of the tile kernel
+    int dmma = 1;         // dense upper blocks of 8 / 16 segments on the FP64 tensor cores (tile kernel MODE 5); 0: CUDA-core FMAs
     int exchangeUnroll = 8;
     int exchangeCtasPerSm = 4;
     // scratch
@@ -178,6 +180,12 @@ using Kernel = void (*)(const WalkParams);
 template <int TB> Kernel tileKernelTB(int mode, int kt) {
     switch (mode) {
         case 0: return dmavm_tile_kernel<TB, 0, 0>;
+        case 5:
+            if constexpr (TB == 3 || TB == 4) {
+                return dmavm_tile_kernel<TB, 5, 0>;
+            } else {
+                return nullptr;
+            }
         case 1:
             return kt == 2 ? dmavm_tile_kernel<TB, 1, 2>
                            : (kt == 4 ? dmavm_tile_kernel<TB, 1, 4> : (kt == 8 ? dmavm_tile_kernel<TB, 1, 8> : dmavm_tile_kernel<TB, 1, 16>));
@@ -276,6 +284,9 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
         const int tSegs = 1 << h.subTileBits;
         p.denseSlots = ((mode == 0 || mode == 2) && tSegs >= 4 && tSegs <= 16 && tSegs <= 2 * h.maxPaths && c->denseSlots) ? 1 : 0;
         if (p.denseSlots) p.maxPaths = std::max(p.maxPaths, tSegs); // the entry area holds one slot per source segment
+        // a complete block on 3 or 4 upper qubits with untouched low levels is a real dense contraction:
+        // (T x T complex) x (T x 32 complex) per sub-tile on the FP64 tensor cores
+        if (mode == 0 && p.denseSlots && (tSegs == 8 || tSegs == 16) && p.segBits == 5 && c->dmma) mode = 5;
         if (mode == 4) { // the entry area holds the concatenated per-sub lists
             int slots = 0;
             for (int sIdx = 0; sIdx < std::min(h.nSub, 8); ++sIdx) {
@@ -324,6 +335,7 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
             kernel<<<gridT, bestW * 32, smemT, c->stream>>>(p);
             CUDA_TRY(cudaGetLastError());
             c->launches++;
+            if (mode == 5) c->tensorCoreLaunches++;
             c->cur ^= 1;
             return;
         }
@@ -510,8 +522,29 @@ int fdd_set_option(fdd_ctx* ctx, const char* key, long value) {
         else if (k == "prefetch") ctx->prefetch = static_cast<int>(value);
         else if (k == "tile_mode") ctx->forceMode = static_cast<int>(value);
         else if (k == "dense_slots") ctx->denseSlots = static_cast<int>(value);
+        else if (k == "dmma") ctx->dmma = static_cast<int>(value);
         else if (k == "exchange_unroll") ctx->exchangeUnroll = static_cast<int>(value);
         else if (k == "exchange_ctas_per_sm") ctx->exchangeCtasPerSm = static_cast<int>(value);
+        else throw std::invalid_argument("unknown option " + k);
+    });
+}
+
+int fdd_get_option(const fdd_ctx* ctx, const char* key, long* value) {
+    return guarded([&] {
+        if (ctx == nullptr || key == nullptr || value == nullptr) throw std::invalid_argument("null argument");
+        const std::string k = key;
+        if (k == "dmavm_variant") *value = ctx->variant;
+        else if (k == "warps_per_cta") *value = ctx->warpsPerCta;
+        else if (k == "ctas_per_sm") *value = ctx->ctasPerSm;
+        else if (k == "prefetch") *value = ctx->prefetch;
+        else if (k == "tile_mode") *value = ctx->forceMode;
+        else if (k == "dense_slots") *value = ctx->denseSlots;
+        else if (k == "dmma") *value = ctx->dmma;
+        else if (k == "exchange_unroll") *value = ctx->exchangeUnroll;
+        else if (k == "exchange_ctas_per_sm") *value = ctx->exchangeCtasPerSm;
+        else if (k == "launches") *value = static_cast<long>(ctx->launches);
+        else if (k == "tensor_core_launches") *value = static_cast<long>(ctx->tensorCoreLaunches);
+        else if (k == "exchanges") *value = static_cast<long>(ctx->exchanges);
         else throw std::invalid_argument("unknown option " + k);
     });
 }

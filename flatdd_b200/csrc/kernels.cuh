@@ -55,6 +55,15 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 __device__ __forceinline__ void st_stream(double2* p, double2 v) {
     asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};\n" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
+// 32-byte streaming store (STG.256): two neighbouring amplitudes
+__device__ __forceinline__ void st_stream2(double2* p, double2 a, double2 b) {
+    asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+}
+// FP64 tensor-core tile: D(8x8) += A(8x4, row) * B(4x8, col).  Fragments (lane l): A[l>>2][l&3], B[l&3][l>>2],
+// D[l>>2][2*(l&3) + {0,1}].  SASS: DMMA.8x8x4.
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
 __device__ __forceinline__ double2 ld_stream(const double2* p) {
     double2 v;
     asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p));
@@ -700,7 +709,7 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
     // phase A stores the entries of a row by source slot (zero weight where the matrix has none), so the
     // T inputs of a sub-tile are loaded into registers once and every output is T FMAs against them,
     // without per-entry slot lookups.  The host enables it when T <= 2 * maxPaths.
-    constexpr bool DENSE_OK = (MODE == 0 || MODE == 2) && T >= 4 && T <= 16;
+    constexpr bool DENSE_OK = (MODE == 0 || MODE == 2 || MODE == 5) && T >= 4 && T <= 16;
     const bool denseTile = DENSE_OK && p.denseSlots != 0;
 
     const uint32_t warpGlobal = blockIdx.x * warpsPerCta + warp;
@@ -835,7 +844,9 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
             for (int t = 0; t < T; ++t) {
                 const uint32_t dep = __shfl_sync(0xffffffffu, myDep, (issueQ << TB) | t);
                 if (lane < segLen) {
-                    cp_async16(ring + (issueSlot * T + t) * 32 + lane, p.y + ((static_cast<uint64_t>(issueBase | dep)) << S) + lane);
+                    // MODE 5 reads the stage as tensor-core fragments: amplitude a of segment t sits at a ^ 2(t & 3)
+                    const int pos = (MODE == 5) ? (lane ^ ((t & 3) << 1)) : lane;
+                    cp_async16(ring + (issueSlot * T + t) * 32 + pos, p.y + ((static_cast<uint64_t>(issueBase | dep)) << S) + lane);
                 }
             }
             issueSlot = (issueSlot + 1 == R) ? 0 : issueSlot + 1;
@@ -851,6 +862,87 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
     for (int r = 0; r < R; ++r) issueNext();
     int useSlot = 0;
 
+    if constexpr (MODE == 5) {
+        // =================== phase B on the FP64 tensor cores (dense upper block, low levels untouched) =========
+        // A sub-tile is a T x 32 complex matrix Y (row = segment slot, column = amplitude of the segment) and
+        // the gate acts as Z = M Y with the T x T block M of phase A.  In real arithmetic
+        //     Zr = Mr Yr + Mi (-Yi),   Zi = Mi Yr + Mr Yi,
+        // i.e. 4 (T/8)(T/4) DMMA.8x8x4 per group of eight amplitude columns instead of 4 T^2 / 32 DFMAs per
+        // column: 8x fewer issue slots for the same flops, and no per-entry shared-memory weight loads
+        // (the block lives in A fragments: 2 (T/8)(T/4) doubles per lane).
+        constexpr int MT = T / 8;             // 8-row blocks of M
+        constexpr int KTL = T / 4;            // 4-column blocks of M
+        constexpr int NT = (T == 16) ? 2 : 4; // 8-column groups computed together (independent DMMA chains)
+        const int fr = lane >> 2;             // fragment row (A, D) / column (B)
+        const int fc = lane & 3;              // fragment column (A) / row (B)
+        double aR[MT][KTL], aI[MT][KTL];
+        auto loadA = [&](int rowBase) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                for (int kt = 0; kt < KTL; ++kt) {
+                    const double2 w = eW[(4 * kt + fc) * 32 + rowBase + 8 * mt + fr];
+                    aR[mt][kt] = w.x;
+                    aI[mt][kt] = w.y;
+                }
+            }
+        };
+        if (p.uniform) loadA(0);
+        for (uint32_t tile = warpGlobal; tile < p.nTiles; tile += warpStride) {
+            const uint32_t base = depositAround(tile, wtMask);
+            if (!p.uniform) {
+                walkTile(base);
+                __syncwarp();
+            }
+            for (int q = 0; q < Q; ++q) {
+                if (!p.uniform) loadA(q << TB);
+                uint32_t dep[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) dep[mt] = __shfl_sync(0xffffffffu, myDep, (q << TB) + 8 * mt + fr);
+                cp_async_wait<R - 1>(); // groups complete in order: the oldest one is this sub-tile
+                __syncwarp();
+                const double2* st = ring + useSlot * T * 32;
+#pragma unroll
+                for (int nt0 = 0; nt0 < 4; nt0 += NT) {
+                    double zr[NT][MT][2], zi[NT][MT][2];
+#pragma unroll
+                    for (int u = 0; u < NT; ++u) {
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) zr[u][mt][0] = zr[u][mt][1] = zi[u][mt][0] = zi[u][mt][1] = 0.0;
+                    }
+#pragma unroll
+                    for (int kt = 0; kt < KTL; ++kt) {
+#pragma unroll
+                        for (int u = 0; u < NT; ++u) {
+                            // B fragment: segment 4 kt + fc, amplitude 8 (nt0 + u) + fr (swizzled like the copy)
+                            const double2 y = st[(4 * kt + fc) * 32 + ((8 * (nt0 + u) + fr) ^ (fc << 1))];
+                            const double nyi = -y.y;
+#pragma unroll
+                            for (int mt = 0; mt < MT; ++mt) {
+                                dmma884(zr[u][mt], aR[mt][kt], y.x);
+                                dmma884(zi[u][mt], aI[mt][kt], y.x);
+                                dmma884(zr[u][mt], aI[mt][kt], nyi);
+                                dmma884(zi[u][mt], aR[mt][kt], y.y);
+                            }
+                        }
+                    }
+                    // D fragment: row 8 mt + fr, amplitudes 8 nt + 2 fc and + 1: 32 contiguous bytes per lane
+#pragma unroll
+                    for (int u = 0; u < NT; ++u) {
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            st_stream2(p.z + ((static_cast<uint64_t>(base | dep[mt])) << S) + 8 * (nt0 + u) + 2 * fc,
+                                       make_double2(zr[u][mt][0], zi[u][mt][0]), make_double2(zr[u][mt][1], zi[u][mt][1]));
+                        }
+                    }
+                }
+                __syncwarp(); // every lane is done with the stage slot before it is refilled
+                useSlot = (useSlot + 1 == R) ? 0 : useSlot + 1;
+                issueNext();
+            }
+        }
+        cp_async_wait<0>();
+    } else {
     for (uint32_t tile = warpGlobal; tile < p.nTiles; tile += warpStride) {
         const uint32_t base = depositAround(tile, wtMask);
         if (!p.uniform) walkTile(base);
@@ -989,6 +1081,7 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
         }
     }
     cp_async_wait<0>();
+    } // MODE != 5
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -33,7 +33,7 @@ def run_cli(circuit: Path, threads: int, fuse: int, extra=()):
                              cwd=cwd, capture_output=True, text=True, check=True).stdout
         raw = np.fromfile(state, dtype="<f8")
         time_lines = next((Path(tmp) / "log" / "results" / "time").glob("*_FlatDD.txt")).read_text().splitlines()
-    stats = json.loads(out[out.rindex("{\n  \"statistics\""):])["statistics"]
+    stats = json.loads(out[out.rindex("\n{\n") + 1:])["statistics"]  # the pretty-printed object is the last thing on stdout
     return out, stats, raw[: raw.size // 2], raw[raw.size // 2:], time_lines
 
 
@@ -59,7 +59,7 @@ def test_cli_final_state_matches_reference(name, threads, fuse, golden):
 def test_cli_shots_and_time_gates():
     """--shots samples on the device (GHZ: only 000000 and 111111), --time-gates reports kernel time."""
     out, stats, re, im, _ = run_cli(ROOT / "tests" / "circuits" / "ghz_n6.qasm", 4, 0, extra=("--shots", "2000", "--seed", "3"))
-    full = json.loads(out[out.rindex("{\n  \"statistics\""):])
+    full = json.loads(out[out.rindex("\n{\n") + 1:])
     assert set(full["samples_top16"].keys()) == {"000000", "111111"}
     assert sum(full["samples_top16"].values()) == 2000
     out, stats, re, im, _ = run_cli(ROOT / "tests" / "circuits" / "mix_n12.qasm", 8, 3, extra=("--time-gates", "--quiet"))

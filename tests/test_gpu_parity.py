@@ -298,3 +298,71 @@ def test_sampling_follows_the_born_rule():
         shots = ctx.sample(4096, seed=1)
     assert set(np.unique(shots)) == {0, (1 << n) - 1}
     assert abs((shots == 0).mean() - 0.5) < 0.05
+
+
+TENSOR_CORE_SHAPES = [
+    # (n, targets, kind): blocks that are complete on 3 or 4 upper qubits with the low five levels untouched
+    (9, [5, 6, 7], "dense"), (10, [5, 6, 7, 8], "dense"), (13, [7, 9, 12], "dense"), (14, [13, 9, 6, 5], "dense"),
+    (16, [15, 14, 13, 12], "dense"), (17, [5, 8, 11, 16], "dense"),
+    (15, [12, 8, 6, 10, 14], "ctrl"),   # control on qubit 12, dense on four others: the block differs from tile to tile
+    (15, [13, 7, 9, 11], "ctrl"),       # same with an 8-segment tile
+    (14, [6, 8, 10, 12], "half"),       # eight sources per output segment inside a 16-segment tile
+]
+
+
+@pytest.mark.parametrize("n,targets,kind", TENSOR_CORE_SHAPES)
+def test_tensor_core_path_vs_numpy_and_fma_path(n, targets, kind):
+    """Tile kernel MODE 5 (DMMA.8x8x4) against numpy, the oracle and the CUDA-core path of the same gate."""
+    rng = np.random.default_rng(77 * n + len(targets))
+    k = len(targets)
+    if kind == "dense":
+        u = B.random_unitary(k, rng)
+    elif kind == "ctrl":
+        u = B.controlled(B.random_unitary(k - 1, rng), 1)
+    else:
+        u = np.kron(B.random_unitary(k - 1, rng), np.array([[0.0, 1.0], [1.0, 0.0]]))  # X on the lowest target
+    gate = B.gate_dd(n, targets, u)
+    yr, yi = B.random_state(n, rng)
+    ref = B.apply_dense(n, targets, u, yr + 1j * yi)
+    out = {}
+    for dmma in (1, 0):
+        with Context(n) as ctx:
+            ctx.set_option("dmma", dmma)
+            ctx.set_state(yr, yi)
+            ctx.apply(gate)
+            ctx.apply(gate)  # both ping-pong directions
+            out[dmma] = ctx.get_state()
+            assert ctx.get_option("tensor_core_launches") == (2 if dmma else 0)
+    ref2 = B.apply_dense(n, targets, u, ref)
+    for dmma in (1, 0):
+        assert np.max(np.abs((out[dmma][0] + 1j * out[dmma][1]) - ref2)) < AMP_TOL
+    assert G.max_amp_err(out[1][0], out[1][1], out[0][0], out[0][1]) < 1e-14
+    if n <= 14:
+        orr, oi = pyoracle.dmavm(gate, yr, yi)
+        orr, oi = pyoracle.dmavm(gate, orr, oi)
+        assert G.max_amp_err(out[1][0], out[1][1], orr, oi) < AMP_TOL
+
+
+def test_tensor_core_path_full_size():
+    """n = 26 (the benchmark's state): dense 4-qubit block on the tensor cores, undone by its adjoint."""
+    n = 26
+    rng = np.random.default_rng(2626)
+    yr, yi = B.random_state(n, rng)
+    targets = [25, 17, 11, 6]
+    u = B.random_unitary(4, rng)
+    with Context(n) as ctx:
+        ctx.set_state(yr, yi)
+        ctx.apply(B.gate_dd(n, targets, u))
+        assert abs(ctx.norm2() - 1.0) < 1e-12
+        probe = rng.integers(0, (1 << n) - 64, size=8)
+        mid = [ctx.get_amplitudes(int(i), 64) for i in probe]
+        ctx.apply(B.gate_dd(n, targets, u.conj().T))
+        assert ctx.get_option("tensor_core_launches") == 2
+        for i in probe:
+            got = ctx.get_amplitudes(int(i), 64)
+            assert np.max(np.abs(got - (yr[i:i + 64] + 1j * yi[i:i + 64]))) < 1e-13
+        # the same gate on the CUDA-core path gives the same intermediate state
+        ctx.set_option("dmma", 0)
+        ctx.apply(B.gate_dd(n, targets, u))
+        for i, want in zip(probe, mid):
+            assert np.max(np.abs(ctx.get_amplitudes(int(i), 64) - want)) < 1e-14
