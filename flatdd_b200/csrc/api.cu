@@ -296,7 +296,7 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
             for (int sIdx = std::min(h.nSub, 8); sIdx < 9; ++sIdx) p.subBase[sIdx] = static_cast<uint8_t>(slots);
             p.maxPaths = std::max(slots, 1);
         }
-        const size_t perWarpT = tileWarpSmem(p.maxPaths, p.stackCap, h.subTileBits, p.uniform);
+        const size_t perWarpT = tileWarpSmem(p.maxPaths, p.stackCap, h.subTileBits, p.uniform, mode == 5);
         const size_t fixedT = fixed + tileCtaSmem(p.maxPaths, p.stackCap, p.uniform);
         const Kernel kernel = tileKernel(h.subTileBits, mode, kt);
         // pick the CTA width that keeps the most warps resident (registers and shared memory both count);
@@ -309,8 +309,10 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
             bestC = hit->second.second;
         } else {
             CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
-            for (int w = 8; w >= 1; --w) {
+            for (int w = 16; w >= 1; --w) {
+                if (mode != 5 && w > 8) continue;
                 if (c->warpsPerCta > 0 && w > c->warpsPerCta) continue;
+                if (mode == 5 && w > kM5MaxWarps) continue; // launch bounds of the tensor-core instantiations
                 const size_t smemW = fixedT + static_cast<size_t>(w) * perWarpT;
                 if (smemW > kSmemBudget) continue;
                 int resident = 0;

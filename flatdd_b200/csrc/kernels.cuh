@@ -22,6 +22,20 @@
 
 #include <type_traits>
 
+// experiment switches of the tensor-core path (tile kernel MODE 5)
+#ifndef FDD_M5_3M
+#define FDD_M5_3M 1   // 1: three real DMMA products per complex product instead of four (measured 0.426 -> 0.417 ms at n = 26)
+#endif
+#ifndef FDD_M5_STAGES
+#define FDD_M5_STAGES 2 // stage slots (sub-tiles) per warp
+#endif
+#ifndef FDD_M5_MAXWARPS
+#define FDD_M5_MAXWARPS 12 // launch bounds: warps per CTA ... (one wide CTA shares one entry area: 12 resident warps instead of 10)
+#endif
+#ifndef FDD_M5_MINCTAS
+#define FDD_M5_MINCTAS 1 // ... and resident CTAs per SM
+#endif
+
 namespace fddb200 {
 
 constexpr int kWarp = 32;
@@ -62,7 +76,7 @@ __device__ __forceinline__ void st_stream2(double2* p, double2 a, double2 b) {
 // FP64 tensor-core tile: D(8x8) += A(8x4, row) * B(4x8, col).  Fragments (lane l): A[l>>2][l&3], B[l&3][l>>2],
 // D[l>>2][2*(l&3) + {0,1}].  SASS: DMMA.8x8x4.
 __device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
 }
 __device__ __forceinline__ double2 ld_stream(const double2* p) {
     double2 v;
@@ -618,22 +632,25 @@ __global__ void __launch_bounds__(128) dmavm_chunk_kernel(const WalkParams p) {
 //         table is applied once per output segment, shuffle last    z_j = sum_s L_s (sum_{i in s} w_ji y_slot(j,i))
 // KT = ELL width of the sub tables rounded up to 2, 4 or 8 (static unrolling); KT = 0 (MODE 3 only)
 // reads the width at run time.  The host picks MODE 1 or 2 by instruction count.
-template <int TB> struct TileShape {
+template <int TB, int MODE = 0> struct TileShape {
     static constexpr int T = 1 << TB;
-    static constexpr int R = (16 / T) < 2 ? 2 : (16 / T);
+    static constexpr int R = MODE == 5 ? FDD_M5_STAGES : ((16 / T) < 2 ? 2 : (16 / T));
     static constexpr int JC = T < 8 ? T : 8;
 };
 // Shared memory of the tile kernel: the entry area (lists + walk stack) and the stage ring.  A uniform
 // gate gives every tile the same lists, so one entry area serves the whole CTA and only the ring is
 // per warp; otherwise every warp has its own entry area.
 __host__ __device__ inline size_t tileEntryBytes(int maxPaths, int stackCap) { return static_cast<size_t>(maxPaths + stackCap) * 32 * 20; }
-__host__ __device__ inline size_t tileRingBytes(int tileBits) {
+// tensor-core path (MODE 5): kM5Stages stage slots of one sub-tile each
+constexpr int kM5Stages = FDD_M5_STAGES;
+constexpr int kM5MaxWarps = FDD_M5_MAXWARPS;
+__host__ __device__ inline size_t tileRingBytes(int tileBits, int tensorCore = 0) {
     const int T = 1 << tileBits;
-    const int R = (16 / T) < 2 ? 2 : (16 / T);
+    const int R = tensorCore ? kM5Stages : ((16 / T) < 2 ? 2 : (16 / T));
     return static_cast<size_t>(R) * T * 512;
 }
-__host__ __device__ inline size_t tileWarpSmem(int maxPaths, int stackCap, int tileBits, int uniform) {
-    return tileRingBytes(tileBits) + (uniform ? 0 : tileEntryBytes(maxPaths, stackCap));
+__host__ __device__ inline size_t tileWarpSmem(int maxPaths, int stackCap, int tileBits, int uniform, int tensorCore = 0) {
+    return tileRingBytes(tileBits, tensorCore) + (uniform ? 0 : tileEntryBytes(maxPaths, stackCap));
 }
 __host__ __device__ inline size_t tileCtaSmem(int maxPaths, int stackCap, int uniform) { return uniform ? tileEntryBytes(maxPaths, stackCap) : 0; }
 
@@ -655,9 +672,10 @@ __device__ __forceinline__ uint32_t depositAround(uint32_t x, uint32_t mask) {
     return x;
 }
 
-template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dmavm_tile_kernel(const WalkParams p) {
-    constexpr int T = TileShape<TB>::T;
-    constexpr int R = TileShape<TB>::R;
+// (MODE 5 keeps more of the gate block in registers: its own launch bounds)
+template <int TB, int MODE, int KT> __global__ void __launch_bounds__(MODE == 5 ? 32 * FDD_M5_MAXWARPS : 256, MODE == 5 ? FDD_M5_MINCTAS : 2) dmavm_tile_kernel(const WalkParams p) {
+    constexpr int T = TileShape<TB, MODE>::T;
+    constexpr int R = TileShape<TB, MODE>::R;
     extern __shared__ __align__(16) unsigned char smemRaw[];
     unsigned char* cursor = smemRaw;
     const UpperNode* upper = p.upper;
@@ -697,7 +715,7 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
     const int warpsPerCta = blockDim.x >> 5;
     unsigned char* ctaEntries = cursor;
     cursor += tileCtaSmem(p.maxPaths, p.stackCap, p.uniform);
-    unsigned char* mine = cursor + static_cast<size_t>(warp) * tileWarpSmem(p.maxPaths, p.stackCap, TB, p.uniform);
+    unsigned char* mine = cursor + static_cast<size_t>(warp) * tileWarpSmem(p.maxPaths, p.stackCap, TB, p.uniform, MODE == 5);
     unsigned char* entries = p.uniform ? ctaEntries : mine;
     const int nSlotsE = p.maxPaths + p.stackCap;
     double2* eW = reinterpret_cast<double2*>(entries);                                               // [nSlotsE][32]
@@ -870,12 +888,18 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
         // i.e. 4 (T/8)(T/4) DMMA.8x8x4 per group of eight amplitude columns instead of 4 T^2 / 32 DFMAs per
         // column: 8x fewer issue slots for the same flops, and no per-entry shared-memory weight loads
         // (the block lives in A fragments: 2 (T/8)(T/4) doubles per lane).
+        // The stage holds whole 512-byte segments (the only request shape that keeps HBM at full rate: 128-byte
+        // column groups per request measured 3.9 TB/s) with an XOR swizzle that makes the fragment reads
+        // conflict-free; the slot is refilled as soon as its last fragments are in registers.
         constexpr int MT = T / 8;             // 8-row blocks of M
         constexpr int KTL = T / 4;            // 4-column blocks of M
-        constexpr int NT = (T == 16) ? 2 : 4; // 8-column groups computed together (independent DMMA chains)
+        constexpr int NT = 2;                 // 8-amplitude column groups computed together (independent DMMA chains)
         const int fr = lane >> 2;             // fragment row (A, D) / column (B)
         const int fc = lane & 3;              // fragment column (A) / row (B)
         double aR[MT][KTL], aI[MT][KTL];
+#if FDD_M5_3M
+        double aS[MT][KTL];
+#endif
         auto loadA = [&](int rowBase) {
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
@@ -884,6 +908,9 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
                     const double2 w = eW[(4 * kt + fc) * 32 + rowBase + 8 * mt + fr];
                     aR[mt][kt] = w.x;
                     aI[mt][kt] = w.y;
+#if FDD_M5_3M
+                    aS[mt][kt] = w.x + w.y;
+#endif
                 }
             }
         };
@@ -904,41 +931,96 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(256, 2) dm
                 const double2* st = ring + useSlot * T * 32;
 #pragma unroll
                 for (int nt0 = 0; nt0 < 4; nt0 += NT) {
+                    // B fragments of this pass: segment 4 kt + fc, amplitude 8 (nt0 + u) + fr (swizzled like the copy)
+                    double2 y[KTL][NT];
+#pragma unroll
+                    for (int kt = 0; kt < KTL; ++kt) {
+#pragma unroll
+                        for (int u = 0; u < NT; ++u) y[kt][u] = st[(4 * kt + fc) * 32 + ((8 * (nt0 + u) + fr) ^ (fc << 1))];
+                    }
+                    if (nt0 + NT == 4) {
+                        // the stage slot is in registers: refill it while the tensor cores work
+                        __syncwarp();
+                        useSlot = (useSlot + 1 == R) ? 0 : useSlot + 1;
+                        issueNext();
+                    }
+                    double2 z0[NT][MT], z1[NT][MT]; // amplitudes 8 nt + 2 fc and + 1 of row 8 mt + fr
+#if FDD_M5_3M
+                    // three real products per complex one: P1 = Mr Yr, P2 = Mi Yi, P3 = (Mr + Mi)(Yr + Yi);
+                    // Zr = P1 - P2, Zi = P3 - P1 - P2
+                    double p1[NT][MT][2], p2[NT][MT][2], p3[NT][MT][2];
+#pragma unroll
+                    for (int u = 0; u < NT; ++u) {
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) p1[u][mt][0] = p1[u][mt][1] = p2[u][mt][0] = p2[u][mt][1] = p3[u][mt][0] = p3[u][mt][1] = 0.0;
+                    }
+#pragma unroll
+                    for (int kt = 0; kt < KTL; ++kt) {
+#pragma unroll
+                        for (int u = 0; u < NT; ++u) {
+                            const double ys = y[kt][u].x + y[kt][u].y;
+#pragma unroll
+                            for (int mt = 0; mt < MT; ++mt) {
+                                dmma884(p1[u][mt], aR[mt][kt], y[kt][u].x);
+                                dmma884(p2[u][mt], aI[mt][kt], y[kt][u].y);
+                                dmma884(p3[u][mt], aS[mt][kt], ys);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < NT; ++u) {
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            z0[u][mt] = make_double2(p1[u][mt][0] - p2[u][mt][0], (p3[u][mt][0] - p1[u][mt][0]) - p2[u][mt][0]);
+                            z1[u][mt] = make_double2(p1[u][mt][1] - p2[u][mt][1], (p3[u][mt][1] - p1[u][mt][1]) - p2[u][mt][1]);
+                        }
+                    }
+#else
                     double zr[NT][MT][2], zi[NT][MT][2];
 #pragma unroll
                     for (int u = 0; u < NT; ++u) {
 #pragma unroll
                         for (int mt = 0; mt < MT; ++mt) zr[u][mt][0] = zr[u][mt][1] = zi[u][mt][0] = zi[u][mt][1] = 0.0;
                     }
+                    // 2 NT MT independent accumulators are touched between two DMMAs on the same one
 #pragma unroll
                     for (int kt = 0; kt < KTL; ++kt) {
 #pragma unroll
                         for (int u = 0; u < NT; ++u) {
-                            // B fragment: segment 4 kt + fc, amplitude 8 (nt0 + u) + fr (swizzled like the copy)
-                            const double2 y = st[(4 * kt + fc) * 32 + ((8 * (nt0 + u) + fr) ^ (fc << 1))];
-                            const double nyi = -y.y;
 #pragma unroll
                             for (int mt = 0; mt < MT; ++mt) {
-                                dmma884(zr[u][mt], aR[mt][kt], y.x);
-                                dmma884(zi[u][mt], aI[mt][kt], y.x);
+                                dmma884(zr[u][mt], aR[mt][kt], y[kt][u].x);
+                                dmma884(zi[u][mt], aI[mt][kt], y[kt][u].x);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < NT; ++u) {
+                            const double nyi = -y[kt][u].y;
+#pragma unroll
+                            for (int mt = 0; mt < MT; ++mt) {
                                 dmma884(zr[u][mt], aI[mt][kt], nyi);
-                                dmma884(zi[u][mt], aR[mt][kt], y.y);
+                                dmma884(zi[u][mt], aR[mt][kt], y[kt][u].y);
                             }
                         }
                     }
-                    // D fragment: row 8 mt + fr, amplitudes 8 nt + 2 fc and + 1: 32 contiguous bytes per lane
 #pragma unroll
                     for (int u = 0; u < NT; ++u) {
 #pragma unroll
                         for (int mt = 0; mt < MT; ++mt) {
-                            st_stream2(p.z + ((static_cast<uint64_t>(base | dep[mt])) << S) + 8 * (nt0 + u) + 2 * fc,
-                                       make_double2(zr[u][mt][0], zi[u][mt][0]), make_double2(zr[u][mt][1], zi[u][mt][1]));
+                            z0[u][mt] = make_double2(zr[u][mt][0], zi[u][mt][0]);
+                            z1[u][mt] = make_double2(zr[u][mt][1], zi[u][mt][1]);
+                        }
+                    }
+#endif
+                    // D fragment: 32 contiguous bytes per lane, 128 per row and store instruction
+#pragma unroll
+                    for (int u = 0; u < NT; ++u) {
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            st_stream2(p.z + ((static_cast<uint64_t>(base | dep[mt])) << S) + 8 * (nt0 + u) + 2 * fc, z0[u][mt], z1[u][mt]);
                         }
                     }
                 }
-                __syncwarp(); // every lane is done with the stage slot before it is refilled
-                useSlot = (useSlot + 1 == R) ? 0 : useSlot + 1;
-                issueNext();
             }
         }
         cp_async_wait<0>();
