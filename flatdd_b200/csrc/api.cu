@@ -97,6 +97,7 @@ struct fdd_ctx {
     float lastMs = 0.0f;
     uint64_t launches = 0;
     uint64_t tensorCoreLaunches = 0;
+    uint64_t flatTableLaunches = 0;
     int smCount = 148;
     // tunables
     int variant = 2;      // 2: tile kernel when the gate allows it, else 1; 1: cp.async ring walk; 0: register walk
@@ -105,6 +106,7 @@ struct fdd_ctx {
     int prefetch = 8;
     int forceMode = -1;   // experiments: force the tile-kernel MODE (1, 2 or 3) where it applies
     int denseSlots = 1;   // experiments: 0 disables the dense register path of the tile kernel
+    int flatTable = 1;    // uniform gates with a sub table per path: flat precombined table (tile kernel MODE 6); 0: MODE 3
     int dmma = 1;         // dense upper blocks of 8 / 16 segments on the FP64 tensor cores (tile kernel MODE 5); 0: CUDA-core FMAs
     int exchangeUnroll = 8;
     int exchangeCtasPerSm = 4;
@@ -191,6 +193,12 @@ template <int TB> Kernel tileKernelTB(int mode, int kt) {
                            : (kt == 4 ? dmavm_tile_kernel<TB, 1, 4> : (kt == 8 ? dmavm_tile_kernel<TB, 1, 8> : dmavm_tile_kernel<TB, 1, 16>));
         case 2: return kt == 2 ? dmavm_tile_kernel<TB, 2, 2> : (kt == 4 ? dmavm_tile_kernel<TB, 2, 4> : dmavm_tile_kernel<TB, 2, 8>);
         case 4: return kt == 2 ? dmavm_tile_kernel<TB, 4, 2> : (kt == 4 ? dmavm_tile_kernel<TB, 4, 4> : dmavm_tile_kernel<TB, 4, 8>);
+        case 6: // kt = entries per row of the flat table
+            if constexpr (TB <= 3) {
+                return kt == 4 ? dmavm_tile_kernel<TB, 6, 4> : (kt == 8 ? dmavm_tile_kernel<TB, 6, 8> : dmavm_tile_kernel<TB, 6, 16>);
+            } else {
+                return nullptr;
+            }
         default:
             return kt == 2 ? dmavm_tile_kernel<TB, 3, 2>
                            : (kt == 4 ? dmavm_tile_kernel<TB, 3, 4> : (kt == 8 ? dmavm_tile_kernel<TB, 3, 8> : dmavm_tile_kernel<TB, 3, 0>));
@@ -275,6 +283,14 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
             }
         }
         if (c->forceMode >= 0 && c->forceMode <= 3 && !allIdentity && (c->forceMode == 3 || (h.nSub == 1 && kt > 0))) mode = c->forceMode;
+        // uniform gate with a sub table per path and few entries per row: flat precombined table (MODE 6)
+        int flatEntries = 0;
+        if (mode == 3 && h.uniform && c->flatTable && h.subTileBits <= 3 && h.maxPaths * h.kMax <= 16 && (h.maxPaths * h.kMax << h.subTileBits) <= 64) {
+            const int e = h.maxPaths * h.kMax;
+            flatEntries = e <= 4 ? 4 : (e <= 8 ? 8 : 16);
+            mode = 6;
+            kt = flatEntries;
+        }
         p.tileBits = h.tileBits;
         p.subTileBits = h.subTileBits;
         p.tileMask = h.tileMask;
@@ -297,7 +313,7 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
             p.maxPaths = std::max(slots, 1);
         }
         const size_t perWarpT = tileWarpSmem(p.maxPaths, p.stackCap, h.subTileBits, p.uniform, mode == 5);
-        const size_t fixedT = fixed + tileCtaSmem(p.maxPaths, p.stackCap, p.uniform);
+        const size_t fixedT = fixed + tileCtaSmem(p.maxPaths, p.stackCap, p.uniform) + (mode == 6 ? tileFlatBytes(h.subTileBits, flatEntries) : 0);
         const Kernel kernel = tileKernel(h.subTileBits, mode, kt);
         // pick the CTA width that keeps the most warps resident (registers and shared memory both count);
         // the answer only depends on (kernel, shared memory shape), so it is cached per context
@@ -338,6 +354,7 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
             CUDA_TRY(cudaGetLastError());
             c->launches++;
             if (mode == 5) c->tensorCoreLaunches++;
+            if (mode == 6) c->flatTableLaunches++;
             c->cur ^= 1;
             return;
         }
@@ -525,6 +542,7 @@ int fdd_set_option(fdd_ctx* ctx, const char* key, long value) {
         else if (k == "tile_mode") ctx->forceMode = static_cast<int>(value);
         else if (k == "dense_slots") ctx->denseSlots = static_cast<int>(value);
         else if (k == "dmma") ctx->dmma = static_cast<int>(value);
+        else if (k == "flat_table") ctx->flatTable = static_cast<int>(value);
         else if (k == "exchange_unroll") ctx->exchangeUnroll = static_cast<int>(value);
         else if (k == "exchange_ctas_per_sm") ctx->exchangeCtasPerSm = static_cast<int>(value);
         else throw std::invalid_argument("unknown option " + k);
@@ -542,6 +560,8 @@ int fdd_get_option(const fdd_ctx* ctx, const char* key, long* value) {
         else if (k == "tile_mode") *value = ctx->forceMode;
         else if (k == "dense_slots") *value = ctx->denseSlots;
         else if (k == "dmma") *value = ctx->dmma;
+        else if (k == "flat_table") *value = ctx->flatTable;
+        else if (k == "flat_table_launches") *value = static_cast<long>(ctx->flatTableLaunches);
         else if (k == "exchange_unroll") *value = ctx->exchangeUnroll;
         else if (k == "exchange_ctas_per_sm") *value = ctx->exchangeCtasPerSm;
         else if (k == "launches") *value = static_cast<long>(ctx->launches);

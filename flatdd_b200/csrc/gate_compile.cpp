@@ -3,6 +3,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
@@ -414,6 +416,20 @@ CompiledGate compileGate(const fdd_matdd& g, int nLocal) {
     return out;
 }
 
+namespace {
+// prices in HBM passes; FLATDD_B200_COST="base,perSegment,crossLane,tensor8,tensor16,walkPerTile" overrides them (experiments)
+struct CostKnobs {
+    double base = 1.2, perSegment = 0.025, crossLane = 0.035, tensor8 = 1.22, tensor16 = 1.29, walkPerTile = 0.7;
+    static CostKnobs fromEnv() {
+        CostKnobs k;
+        if (const char* e = std::getenv("FLATDD_B200_COST")) {
+            std::sscanf(e, "%lf,%lf,%lf,%lf,%lf,%lf", &k.base, &k.perSegment, &k.crossLane, &k.tensor8, &k.tensor16, &k.walkPerTile);
+        }
+        return k;
+    }
+};
+} // namespace
+
 double costGpuNs(const CompiledGate& c, double hbmGBs, double fp64GFlops) {
     // Time of one launch as a multiple of the HBM time of one read + one write pass (0.33 ms at n = 26).
     // Two regimes, both fitted to the tile kernel on B200 (profiles/r01_cost_model_fit.txt):
@@ -431,10 +447,17 @@ double costGpuNs(const CompiledGate& c, double hbmGBs, double fp64GFlops) {
     const bool registerPath = c.tileable && c.subTileBits >= 2 && c.subTileBits <= 4 && (1 << c.subTileBits) <= 2 * c.maxPaths;
     const bool knownFast = c.tileable && c.uniform && (c.allIdentitySubs || c.nSub == 1) &&
                            c.kTrue <= (c.maxPaths > 4 ? 4 : 8) && (registerPath || c.maxPaths <= 4);
+    // complete block on 3 / 4 upper qubits with untouched low levels: the tensor-core path (tile kernel MODE 5),
+    // measured 0.40 / 0.42 ms whatever the block holds
+    const bool tensorPath = registerPath && c.allIdentitySubs && c.subTileBits >= 3;
+    static const CostKnobs knobs = CostKnobs::fromEnv();
     double factor;
     if (knownFast) {
-        factor = 1.2 + (registerPath ? 0.025 * (1 << c.subTileBits) : 0.0);
-        if (c.kTrue > 1) factor += 0.035 * c.kTrue * std::max(1.0, c.maxPaths / 4.0); // (16,2): +0.28, (16,4): +0.56 measured
+        factor = knobs.base + (registerPath ? knobs.perSegment * (1 << c.subTileBits) : 0.0);
+        if (tensorPath) factor = c.subTileBits == 3 ? knobs.tensor8 : knobs.tensor16;
+        if (c.kTrue > 1) factor += knobs.crossLane * c.kTrue * std::max(1.0, c.maxPaths / 4.0); // (16,2): +0.28, (16,4): +0.56 measured
+    } else if (tensorPath && c.tileable) {
+        factor = (c.subTileBits == 3 ? knobs.tensor8 : knobs.tensor16) + knobs.walkPerTile; // the block is re-read from the walk of every tile
     } else {
         const double instrPerSeg = 40.0 + c.maxPaths * (14.0 + 16.0 * c.kTrue) + 12.0 * c.upperDepth * c.maxPaths / 4.0;
         const double issueNs = (amps / 32.0) * instrPerSeg / (148.0 * 4.0 * 1.8 * 0.6);

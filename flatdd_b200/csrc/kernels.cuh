@@ -630,6 +630,10 @@ __global__ void __launch_bounds__(128) dmavm_chunk_kernel(const WalkParams p) {
 // MODE 3: sub table depends on the path, gather first               z_j = sum_i w_ji (L_sub(j,i) y_slot(j,i))
 // MODE 4: like MODE 3 but the entry lists are kept per sub table (at most 8 tables, 15 slots), so each
 //         table is applied once per output segment, shuffle last    z_j = sum_s L_s (sum_{i in s} w_ji y_slot(j,i))
+// MODE 5: MODE 0 with a complete block of 8 / 16 sources per segment on the FP64 tensor cores (DMMA.8x8x4)
+// MODE 6: MODE 3 for uniform gates: the products w_ji L_sub(j,i) are formed once per CTA into a flat table of
+//         KT = paths x ELL width entries per row (lane-private weight, source = slot * 32 + column), so
+//         phase B is one multiply-add per entry: no per-path sub-table lookups, no weight products
 // KT = ELL width of the sub tables rounded up to 2, 4 or 8 (static unrolling); KT = 0 (MODE 3 only)
 // reads the width at run time.  The host picks MODE 1 or 2 by instruction count.
 template <int TB, int MODE = 0> struct TileShape {
@@ -653,6 +657,8 @@ __host__ __device__ inline size_t tileWarpSmem(int maxPaths, int stackCap, int t
     return tileRingBytes(tileBits, tensorCore) + (uniform ? 0 : tileEntryBytes(maxPaths, stackCap));
 }
 __host__ __device__ inline size_t tileCtaSmem(int maxPaths, int stackCap, int uniform) { return uniform ? tileEntryBytes(maxPaths, stackCap) : 0; }
+// MODE 6: the flat table of a uniform gate, [T rows][E entries][32 lanes] of (weight 16 B, source 2 B)
+__host__ __device__ inline size_t tileFlatBytes(int tileBits, int entries) { return (static_cast<size_t>(1) << tileBits) * entries * 32 * 18; }
 
 __device__ __forceinline__ uint32_t depositBits(uint32_t x, uint32_t mask) { // pdep
     uint32_t out = 0;
@@ -847,6 +853,33 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(MODE == 5 
     if (p.uniform) {
         // every tile sees the same lists: warp 0 walks once for the whole CTA
         if (warp == 0) walkTile(0u);
+        __syncthreads();
+    }
+    // MODE 6: flat table behind the per-warp areas, built by the whole CTA from the lists of sub-tile 0
+    double2* flatW = nullptr;
+    uint16_t* flatC = nullptr;
+    if constexpr (MODE == 6) {
+        constexpr int E = KT;
+        unsigned char* flat = cursor + static_cast<size_t>(warpsPerCta) * tileWarpSmem(p.maxPaths, p.stackCap, TB, p.uniform);
+        flatW = reinterpret_cast<double2*>(flat);
+        flatC = reinterpret_cast<uint16_t*>(flat + static_cast<size_t>(T) * E * 32 * 16);
+        const int kw = p.kMax; // ELL width of the tables as uploaded
+        for (int idx = warp; idx < T * E; idx += warpsPerCta) {
+            const int t = idx / E;
+            const int e = idx - t * E;
+            const int i = e / kw;
+            const int k = e - i * kw;
+            double2 w = make_double2(0.0, 0.0);
+            uint32_t src = static_cast<uint32_t>(t) * 32u + static_cast<uint32_t>(lane);
+            if (i < P) {
+                const uint32_t pk = ePack[i * 32 + t];
+                const int at = (static_cast<int>(pk >> 8) * kw + k) * 32 + lane;
+                w = cmul(eW[i * 32 + t], subW[at]);
+                src = (pk & 31u) * 32u + subCol[at];
+            }
+            flatW[idx * 32 + lane] = w;
+            flatC[idx * 32 + lane] = static_cast<uint16_t>(src);
+        }
         __syncthreads();
     }
     if (warpGlobal >= p.nTiles) return;
@@ -1096,6 +1129,17 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(MODE == 5 
 #pragma unroll
                             for (int k = 0; k < KR; ++k) cmac(t, Lw[k], src[Lc[k]]);
                             cmac(acc[a], w, t);
+                        }
+                    }
+                } else if (MODE == 6) {
+                    constexpr int E = KT > 0 ? KT : 1;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+#pragma unroll
+                        for (int a = 0; a < NACC; ++a) {
+                            const int t = (j0 + a) & (T - 1); // row inside the sub-tile (compile-time after unrolling)
+                            const int at = (t * E + e) * 32 + lane;
+                            cmac(acc[a], flatW[at], stageOf(a)[flatC[at]]);
                         }
                     }
                 } else if (MODE == 4) {

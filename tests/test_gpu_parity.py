@@ -366,3 +366,31 @@ def test_tensor_core_path_full_size():
         ctx.apply(B.gate_dd(n, targets, u))
         for i, want in zip(probe, mid):
             assert np.max(np.abs(ctx.get_amplitudes(int(i), 64) - want)) < 1e-14
+
+
+FLAT_TABLE_SHAPES = [
+    # (n, targets, expect MODE 6): dense blocks that mix upper and lane qubits, so the sub table depends on the path
+    (12, [3, 8], True), (13, [1, 4, 9], True), (14, [2, 7, 11], True), (14, [0, 3, 9, 12], True), (16, [4, 15], True),
+    (15, [4, 8, 10, 13], False),  # 8 paths x 2 on an 8-segment tile: table too large, stays on MODE 3
+]
+
+
+@pytest.mark.parametrize("n,targets,flat", FLAT_TABLE_SHAPES)
+def test_flat_table_path_vs_numpy_and_mode3(n, targets, flat):
+    """Tile kernel MODE 6 (flat precombined table of a uniform gate) against numpy and against MODE 3."""
+    rng = np.random.default_rng(31 * n + len(targets))
+    u = B.random_unitary(len(targets), rng)
+    gate = B.gate_dd(n, targets, u)
+    yr, yi = B.random_state(n, rng)
+    ref = B.apply_dense(n, targets, u, B.apply_dense(n, targets, u, yr + 1j * yi))
+    out = {}
+    for on in (1, 0):
+        with Context(n) as ctx:
+            ctx.set_option("flat_table", on)
+            ctx.set_state(yr, yi)
+            ctx.apply(gate)
+            ctx.apply(gate)
+            out[on] = ctx.get_state()
+            assert ctx.get_option("flat_table_launches") == (2 if (on and flat) else 0)
+        assert np.max(np.abs((out[on][0] + 1j * out[on][1]) - ref)) < AMP_TOL
+    assert G.max_amp_err(out[1][0], out[1][1], out[0][0], out[0][1]) < 1e-14
