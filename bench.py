@@ -238,6 +238,9 @@ def gpu_arm(args) -> int:
         uid = [lib.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0, device=device)
         ctx.comm_init(uid[0])
+    for kv in args.option:
+        key, value = kv.split("=")
+        ctx.set_option(key, int(value))
     stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
     steps = []  # ("g", [compiled gates of one schedule segment]) | ("x", global bit, local bit) | ("r", a, b)
     for r in records[1:]:
@@ -431,6 +434,7 @@ def main() -> int:
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default=WORKLOAD, help="supremacy_n26 (default), supremacy_n20, knn_n31_f0, ... (needs its boundary trace)")
     ap.add_argument("--exchange-method", type=int, default=0, help="0 = peer-memory kernel, 1 = NCCL send/recv")
+    ap.add_argument("--option", action="append", default=[], help="experiments: library tunable key=value (fdd_set_option), repeatable")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

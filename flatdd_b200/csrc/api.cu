@@ -66,6 +66,7 @@ template <class F> int guarded(F&& body) {
 
 constexpr size_t kSmemBudget = 227 * 1024;
 constexpr size_t kTableSmemLimit = 96 * 1024;
+constexpr int kMaxContextBits = 10; // context table of the tensor-core path: at most 1024 blocks (4 MiB at 16 x 16)
 
 } // namespace
 
@@ -79,6 +80,7 @@ struct fdd_gate {
     int32_t* dSubK = nullptr;
     uint8_t* dSubFlags = nullptr;
     void* dBlob = nullptr; // one allocation holding all of the above
+    mutable double2* dCtx = nullptr; // tensor-core path: blocks of a non-uniform gate per value of its context bits (built at the first launch)
 };
 
 struct fdd_ctx {
@@ -98,6 +100,7 @@ struct fdd_ctx {
     uint64_t launches = 0;
     uint64_t tensorCoreLaunches = 0;
     uint64_t flatTableLaunches = 0;
+    uint64_t contextLaunches = 0;
     int smCount = 148;
     // tunables
     int variant = 2;      // 2: tile kernel when the gate allows it, else 1; 1: cp.async ring walk; 0: register walk
@@ -107,6 +110,8 @@ struct fdd_ctx {
     int forceMode = -1;   // experiments: force the tile-kernel MODE (1, 2 or 3) where it applies
     int denseSlots = 1;   // experiments: 0 disables the dense register path of the tile kernel
     int flatTable = 1;    // uniform gates with a sub table per path: flat precombined table (tile kernel MODE 6); 0: MODE 3
+    int contextTable = 1; // tensor-core path of non-uniform gates: look the block up per tile instead of walking the gate per tile
+    int pdl = 0;          // 1: tile kernel launches overlap their prologue with the tail of the previous launch (measured: no gain)
     int dmma = 1;         // dense upper blocks of 8 / 16 segments on the FP64 tensor cores (tile kernel MODE 5); 0: CUDA-core FMAs
     int exchangeUnroll = 8;
     int exchangeCtasPerSm = 4;
@@ -312,24 +317,20 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
             for (int sIdx = std::min(h.nSub, 8); sIdx < 9; ++sIdx) p.subBase[sIdx] = static_cast<uint8_t>(slots);
             p.maxPaths = std::max(slots, 1);
         }
-        const size_t perWarpT = tileWarpSmem(p.maxPaths, p.stackCap, h.subTileBits, p.uniform, mode == 5);
-        const size_t fixedT = fixed + tileCtaSmem(p.maxPaths, p.stackCap, p.uniform) + (mode == 6 ? tileFlatBytes(h.subTileBits, flatEntries) : 0);
         const Kernel kernel = tileKernel(h.subTileBits, mode, kt);
         // pick the CTA width that keeps the most warps resident (registers and shared memory both count);
         // the answer only depends on (kernel, shared memory shape), so it is cached per context
-        int bestW = 0, bestC = 0;
-        const auto key = std::make_tuple(reinterpret_cast<const void*>(kernel), fixedT, perWarpT, c->warpsPerCta, c->ctasPerSm);
-        const auto hit = c->launchShapes.find(key);
-        if (hit != c->launchShapes.end()) {
-            bestW = hit->second.first;
-            bestC = hit->second.second;
-        } else {
+        auto pickShape = [&](size_t fixedBytes, size_t perWarpBytes) {
+            int bestW = 0, bestC = 0;
+            const auto key = std::make_tuple(reinterpret_cast<const void*>(kernel), fixedBytes, perWarpBytes, c->warpsPerCta, c->ctasPerSm);
+            const auto hit = c->launchShapes.find(key);
+            if (hit != c->launchShapes.end()) return hit->second;
             CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
             for (int w = 16; w >= 1; --w) {
                 if (mode != 5 && w > 8) continue;
                 if (c->warpsPerCta > 0 && w > c->warpsPerCta) continue;
                 if (mode == 5 && w > kM5MaxWarps) continue; // launch bounds of the tensor-core instantiations
-                const size_t smemW = fixedT + static_cast<size_t>(w) * perWarpT;
+                const size_t smemW = fixedBytes + static_cast<size_t>(w) * perWarpBytes;
                 if (smemW > kSmemBudget) continue;
                 int resident = 0;
                 CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, w * 32, smemW));
@@ -342,17 +343,71 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
             c->launchShapes.emplace(key, std::make_pair(bestW, bestC));
             if (std::getenv("FLATDD_B200_DEBUG") != nullptr) {
                 std::fprintf(stderr, "[flatdd_b200] tile kernel TB=%d mode=%d kt=%d: %d warps/CTA x %d CTAs/SM, smem %zu B (cta %zu + %zu per warp), paths %d, uniform %d, dense %d\n",
-                             h.subTileBits, mode, kt, bestW, bestC, fixedT + bestW * perWarpT, fixedT, perWarpT, p.maxPaths, p.uniform, p.denseSlots);
+                             h.subTileBits, mode, kt, bestW, bestC, fixedBytes + bestW * perWarpBytes, fixedBytes, perWarpBytes, p.maxPaths, p.uniform, p.denseSlots);
             }
-        }
-        if (bestW > 0) {
-            const size_t smemT = fixedT + static_cast<size_t>(bestW) * perWarpT;
-            const uint32_t ctasWantedT = (p.nTiles + bestW - 1) / bestW;
-            const int gridT = static_cast<int>(std::max<uint32_t>(1, std::min<uint32_t>(ctasWantedT, static_cast<uint32_t>(c->smCount * bestC))));
-            Timed t(c);
-            kernel<<<gridT, bestW * 32, smemT, c->stream>>>(p);
+            return std::make_pair(bestW, bestC);
+        };
+        auto launchTile = [&](const WalkParams& params, size_t fixedBytes, size_t perWarpBytes, uint32_t warpItems) {
+            const auto shape = pickShape(fixedBytes, perWarpBytes);
+            if (shape.first == 0) return false;
+            const size_t smemT = fixedBytes + static_cast<size_t>(shape.first) * perWarpBytes;
+            const uint32_t ctasWantedT = (warpItems + shape.first - 1) / shape.first;
+            const int gridT = static_cast<int>(std::max<uint32_t>(1, std::min<uint32_t>(ctasWantedT, static_cast<uint32_t>(c->smCount * shape.second))));
+            if (c->pdl) {
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(static_cast<unsigned>(gridT));
+                cfg.blockDim = dim3(static_cast<unsigned>(shape.first * 32));
+                cfg.dynamicSmemBytes = smemT;
+                cfg.stream = c->stream;
+                cudaLaunchAttribute attr{};
+                attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr.val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = &attr;
+                cfg.numAttrs = 1;
+                CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, params));
+            } else {
+                kernel<<<gridT, shape.first * 32, smemT, c->stream>>>(params);
+            }
             CUDA_TRY(cudaGetLastError());
             c->launches++;
+            return true;
+        };
+        size_t perWarpT = tileWarpSmem(p.maxPaths, p.stackCap, h.subTileBits, p.uniform, mode == 5);
+        size_t fixedT = fixed + tileCtaSmem(p.maxPaths, p.stackCap, p.uniform) + (mode == 6 ? tileFlatBytes(h.subTileBits, flatEntries) : 0);
+        Timed t(c);
+        // tensor-core path of a gate whose block depends on a few diagonal upper qubits (controls, phases): walk every
+        // value of those bits once into a table (cached with the compiled gate) instead of once per warp tile
+        const int ctxBits = __builtin_popcount(h.ctxMask);
+        if (mode == 5 && c->contextTable && ctxBits <= kMaxContextBits) {
+            // (a uniform gate is the case of zero context bits: one block, and the launch itself has no prologue)
+            bool ok = true;
+            if (g->dCtx == nullptr) {
+                WalkParams pre = p;
+                pre.uniform = 0; // every warp of the pre-pass walks into its own entry area
+                const size_t prePerWarp = tileWarpSmem(p.maxPaths, p.stackCap, h.subTileBits, 0, 1);
+                pre.ctxPhase = 1;
+                pre.ctxMask = h.ctxMask;
+                pre.nCtx = 1 << ctxBits;
+                CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&g->dCtx), (sizeof(double2) * tSegs * tSegs) << ctxBits, c->stream));
+                pre.ctxTable = g->dCtx;
+                ok = launchTile(pre, fixed, prePerWarp, static_cast<uint32_t>(pre.nCtx));
+                if (!ok) {
+                    cudaFreeAsync(g->dCtx, c->stream);
+                    g->dCtx = nullptr;
+                }
+            }
+            if (ok) {
+                p.ctxPhase = 2;
+                p.ctxMask = h.ctxMask;
+                p.nCtx = 1 << ctxBits;
+                p.ctxTable = g->dCtx;
+                p.tablesInSmem = 0; // nothing walks the gate in this launch
+                fixedT = 0;
+                perWarpT = tileRingBytes(h.subTileBits, 1);
+                c->contextLaunches++;
+            }
+        }
+        if (launchTile(p, fixedT, perWarpT, p.nTiles)) {
             if (mode == 5) c->tensorCoreLaunches++;
             if (mode == 6) c->flatTableLaunches++;
             c->cur ^= 1;
@@ -406,6 +461,14 @@ void launchWalk(fdd_ctx* c, const fdd_gate* g) {
 
 void freeGate(fdd_gate* g, cudaStream_t stream) {
     if (g == nullptr) return;
+    if (g->dCtx != nullptr) {
+        cudaSetDevice(g->device);
+        if (stream != nullptr) {
+            cudaFreeAsync(g->dCtx, stream);
+        } else {
+            cudaFree(g->dCtx);
+        }
+    }
     if (g->dBlob != nullptr) {
         cudaSetDevice(g->device);
         if (stream != nullptr) {
@@ -542,6 +605,8 @@ int fdd_set_option(fdd_ctx* ctx, const char* key, long value) {
         else if (k == "tile_mode") ctx->forceMode = static_cast<int>(value);
         else if (k == "dense_slots") ctx->denseSlots = static_cast<int>(value);
         else if (k == "dmma") ctx->dmma = static_cast<int>(value);
+        else if (k == "pdl") ctx->pdl = static_cast<int>(value);
+        else if (k == "context_table") ctx->contextTable = static_cast<int>(value);
         else if (k == "flat_table") ctx->flatTable = static_cast<int>(value);
         else if (k == "exchange_unroll") ctx->exchangeUnroll = static_cast<int>(value);
         else if (k == "exchange_ctas_per_sm") ctx->exchangeCtasPerSm = static_cast<int>(value);
@@ -560,6 +625,9 @@ int fdd_get_option(const fdd_ctx* ctx, const char* key, long* value) {
         else if (k == "tile_mode") *value = ctx->forceMode;
         else if (k == "dense_slots") *value = ctx->denseSlots;
         else if (k == "dmma") *value = ctx->dmma;
+        else if (k == "pdl") *value = ctx->pdl;
+        else if (k == "context_table") *value = ctx->contextTable;
+        else if (k == "context_table_launches") *value = static_cast<long>(ctx->contextLaunches);
         else if (k == "flat_table") *value = ctx->flatTable;
         else if (k == "flat_table_launches") *value = static_cast<long>(ctx->flatTableLaunches);
         else if (k == "exchange_unroll") *value = ctx->exchangeUnroll;
@@ -839,6 +907,7 @@ static long gateFact(const CompiledGate& h, const std::string& k) {
     if (k == "fill_mask") return static_cast<long>(h.fillMask);
     if (k == "sub_tile_bits") return h.subTileBits;
     if (k == "non_diag_upper") return h.nonDiagUpper;
+    if (k == "context_bits") return __builtin_popcount(h.ctxMask);
     return -1;
 }
 

@@ -407,7 +407,10 @@ CompiledGate compileGate(const fdd_matdd& g, int nLocal) {
             for (UpperNode& nd : out.upper) {
                 const int sh = nd.level - S;
                 nd.slotBit = (sh < 32 && ((mask >> sh) & 1u)) ? __builtin_popcount(mask & ((1u << sh) - 1u)) : -1;
-                if (nd.slotBit < 0) out.uniform = false;
+                if (nd.slotBit < 0) {
+                    out.uniform = false;
+                    if (sh < localSegBits) out.ctxMask |= 1u << sh; // levels above the shard are constant per rank
+                }
             }
         } else {
             for (UpperNode& nd : out.upper) nd.slotBit = -1;

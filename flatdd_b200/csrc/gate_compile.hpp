@@ -75,6 +75,8 @@ struct CompiledGate {
     int nonDiagUpper = 0; // upper levels with an off-diagonal successor
     bool uniform = false; // tileable and every upper node sits on a tile bit: all sub-tiles see the same entries
     uint64_t nonDiagMask = 0; // bit v set when level v has an off-diagonal successor (all levels)
+    uint32_t ctxMask = 0;     // tileable gates: local segment-index bits of the upper levels outside the tile that still have nodes
+                              // (diagonal levels the block depends on); 0 for uniform gates
 };
 
 // Throws std::runtime_error with a message on malformed input.

@@ -238,6 +238,13 @@ struct WalkParams {
     uint8_t subBase[9];
     int uniform;                      // tile kernel: the entry lists do not depend on the tile (walk once per warp)
     int denseSlots;                   // tile kernel: entries are stored by source slot (T per row, zero weight when absent)
+    // tensor-core path, gate not uniform: the block depends on the index bits `ctxMask` (diagonal upper levels
+    // outside the tile: controls, phases).  ctxPhase 1 = walk every value of those bits once and store the
+    // T x T blocks in ctxTable; ctxPhase 2 = the DMAVM launch looks its block up instead of walking per tile.
+    double2* ctxTable;                // [nCtx][T columns][T rows]
+    uint32_t ctxMask;
+    int nCtx;
+    int ctxPhase;
 };
 
 // Bytes of shared memory one warp needs.
@@ -682,6 +689,9 @@ __device__ __forceinline__ uint32_t depositAround(uint32_t x, uint32_t mask) {
 template <int TB, int MODE, int KT> __global__ void __launch_bounds__(MODE == 5 ? 32 * FDD_M5_MAXWARPS : 256, MODE == 5 ? FDD_M5_MINCTAS : 2) dmavm_tile_kernel(const WalkParams p) {
     constexpr int T = TileShape<TB, MODE>::T;
     constexpr int R = TileShape<TB, MODE>::R;
+    // programmatic dependent launch: let the next launch of the stream start its prologue (table staging,
+    // walk of a uniform gate) while this grid drains; it waits below before it touches the state
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ __align__(16) unsigned char smemRaw[];
     unsigned char* cursor = smemRaw;
     const UpperNode* upper = p.upper;
@@ -720,13 +730,14 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(MODE == 5 
     const int warp = threadIdx.x >> 5;
     const int warpsPerCta = blockDim.x >> 5;
     unsigned char* ctaEntries = cursor;
-    cursor += tileCtaSmem(p.maxPaths, p.stackCap, p.uniform);
-    unsigned char* mine = cursor + static_cast<size_t>(warp) * tileWarpSmem(p.maxPaths, p.stackCap, TB, p.uniform, MODE == 5);
+    const bool lookup = MODE == 5 && p.ctxPhase == 2; // blocks come from the context table: no entry area at all
+    if (!lookup) cursor += tileCtaSmem(p.maxPaths, p.stackCap, p.uniform);
+    unsigned char* mine = cursor + static_cast<size_t>(warp) * (lookup ? tileRingBytes(TB, 1) : tileWarpSmem(p.maxPaths, p.stackCap, TB, p.uniform, MODE == 5));
     unsigned char* entries = p.uniform ? ctaEntries : mine;
     const int nSlotsE = p.maxPaths + p.stackCap;
     double2* eW = reinterpret_cast<double2*>(entries);                                               // [nSlotsE][32]
     uint32_t* ePack = reinterpret_cast<uint32_t*>(entries + static_cast<size_t>(nSlotsE) * 32 * 16); // [nSlotsE][32]
-    double2* ring = reinterpret_cast<double2*>(p.uniform ? mine : mine + tileEntryBytes(p.maxPaths, p.stackCap)); // [R][T][32]
+    double2* ring = reinterpret_cast<double2*>((p.uniform || lookup) ? mine : mine + tileEntryBytes(p.maxPaths, p.stackCap)); // [R][T][32]
     const int stackBase = p.maxPaths;
     const int P = p.maxPaths;
     // Dense register path (MODE 0 / 2: weights do not depend on the lane; 4..16 segments per sub-tile):
@@ -855,6 +866,20 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(MODE == 5 
         if (warp == 0) walkTile(0u);
         __syncthreads();
     }
+    if constexpr (MODE == 5) {
+        if (p.ctxPhase == 1) {
+            // context pre-pass: one walk per value of the context bits, rows = lanes 0..T-1 (sub-tile 0 of the warp tile)
+            for (uint32_t ctx = blockIdx.x * warpsPerCta + warp; ctx < static_cast<uint32_t>(p.nCtx); ctx += gridDim.x * warpsPerCta) {
+                walkTile(depositBits(ctx, p.ctxMask));
+                __syncwarp();
+                if (lane < T) {
+                    for (int i = 0; i < T; ++i) p.ctxTable[(static_cast<size_t>(ctx) * T + i) * T + lane] = eW[i * 32 + lane];
+                }
+                __syncwarp();
+            }
+            return;
+        }
+    }
     // MODE 6: flat table behind the per-warp areas, built by the whole CTA from the lists of sub-tile 0
     double2* flatW = nullptr;
     uint16_t* flatC = nullptr;
@@ -884,6 +909,8 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(MODE == 5 
     }
     if (warpGlobal >= p.nTiles) return;
 
+    // everything above read only the gate tables; the state buffers belong to the previous launch until here
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // ---- copy pipeline state: running sub-tile counter over all warp tiles of this warp ---------
     uint32_t issueTile = warpGlobal;
     uint32_t issueBase = depositAround(issueTile, wtMask);
@@ -947,15 +974,36 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(MODE == 5 
                 }
             }
         };
+        auto lookupA = [&](uint32_t segBits) {
+            uint32_t ctx = 0;
+            int at = 0;
+            for (uint32_t m = p.ctxMask; m != 0; m &= m - 1, ++at) {
+                if (segBits & (m & (0u - m))) ctx |= 1u << at;
+            }
+            const double2* blk = p.ctxTable + static_cast<size_t>(ctx) * T * T;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                for (int kt = 0; kt < KTL; ++kt) {
+                    const double2 w = __ldg(blk + (4 * kt + fc) * T + 8 * mt + fr);
+                    aR[mt][kt] = w.x;
+                    aI[mt][kt] = w.y;
+#if FDD_M5_3M
+                    aS[mt][kt] = w.x + w.y;
+#endif
+                }
+            }
+        };
         if (p.uniform) loadA(0);
         for (uint32_t tile = warpGlobal; tile < p.nTiles; tile += warpStride) {
             const uint32_t base = depositAround(tile, wtMask);
-            if (!p.uniform) {
+            if (!p.uniform && !lookup) {
                 walkTile(base);
                 __syncwarp();
             }
             for (int q = 0; q < Q; ++q) {
-                if (!p.uniform) loadA(q << TB);
+                if (lookup) lookupA(base | depositBits(static_cast<uint32_t>(q), p.fillMask));
+                else if (!p.uniform) loadA(q << TB);
                 uint32_t dep[MT];
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) dep[mt] = __shfl_sync(0xffffffffu, myDep, (q << TB) + 8 * mt + fr);

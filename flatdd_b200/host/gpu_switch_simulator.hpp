@@ -36,6 +36,8 @@
 #include <chrono>
 #include <cmath>
 #include <cstddef>
+#include <cstdio>
+#include <cstdlib>
 #include <iostream>
 #include <memory>
 #include <stdexcept>
@@ -50,9 +52,9 @@ struct FusionPolicy {
     int maxNodes = 4096;         // bound on the flat table of a fused gate
     // fuse == 4 (dependency-graph fusion): a block may hold at most this many dense qubits
     // (non-zeros per row <= 2^maxDenseQubits) and this many non-diagonal qubits above the warp lanes
-    int maxDenseQubits = 2;
-    int maxTileQubits = 5;
-    double budgetFactor = 1.8;   // accept a block while its modelled time <= budgetFactor x the HBM time of one pass
+    int maxDenseQubits = 4;      // (4 dense qubits on <= 4 tile qubits: the tensor-core path, ~1.3 passes whatever the block holds)
+    int maxTileQubits = 4;
+    double budgetFactor = 2.2;   // accept a block while its modelled time <= budgetFactor x the HBM time of one pass
 };
 
 template <class Package, class Qc, class DdOps, class WeightTraits> class GpuSwitchSimulator {
@@ -63,6 +65,10 @@ public:
 
     GpuSwitchSimulator(std::unique_ptr<Qc>&& circuit, ArrayBackend* backend_) : qc(std::move(circuit)), backend(backend_) {
         dd->resize(qc->getNqubits());
+        // experiments: FLATDD_B200_FUSE4="maxDenseQubits,maxTileQubits,budgetFactor" overrides the fuse == 4 policy
+        if (const char* e = std::getenv("FLATDD_B200_FUSE4")) {
+            std::sscanf(e, "%d,%d,%lf", &policy.maxDenseQubits, &policy.maxTileQubits, &policy.budgetFactor);
+        }
     }
 
     // ---- reference surface ------------------------------------------------------------------

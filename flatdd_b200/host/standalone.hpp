@@ -1,0 +1,764 @@
+// standalone.hpp — a host front end that needs nothing of the reference at build or run time
+// (SURVEY.md section 8f, rows N1 and N2): an OpenQASM 2 reader, the gate matrices, a dense-block
+// fusion pass and a builder that emits every (fused) gate as a flat matrix DD for the C-ABI.
+//
+// Policy ("start flat when the state fits HBM", N2): there is no vector-DD phase.  The state
+// starts as the flat array of |0...0> on the device (the conversion kernel expands the
+// n-node DD of that state) and every gate is a DMAVM launch.  What the reference's DD phase
+// contributes — tolerance snapping of amplitudes below ~1e-13 (include/dd/RealNumber.hpp) —
+// is absent, so final states agree with the reference within its own tolerance, not bit for bit.
+//
+// Fusion (N1): operations are multiplied into dense blocks with pairwise disjoint qubit sets (blocks
+// on disjoint qubits commute, so several stay open at once) while a block
+// stays on at most `maxBlockQubits` qubits of which at most `maxNonDiagonal` are non-diagonal
+// (the quantity that sizes a tile of the DMAVM kernel: a block that is complete on <= 4 upper
+// qubits runs on the tensor-core path at ~1.3 HBM passes whatever it holds).  Diagonal qubits
+// (controls, phase gates) ride along for free.  This replaces the reference's DD-multiply based
+// greedy pass (src/SwitchSimulator.cpp:267-340), which needs the DD package.
+//
+// Gate matrices follow the reference (include/dd/GateMatrixDefinitions.hpp:29-135) including
+// global phases; two-target gates take the first listed qubit as the high bit of the 4x4 matrix.
+#pragma once
+
+#include "array_backend.hpp"
+
+#include <algorithm>
+#include <array>
+#include <cctype>
+#include <chrono>
+#include <cmath>
+#include <complex>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <map>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace fddb200::standalone {
+
+using cplx = std::complex<double>;
+
+// ------------------------------------------------------------------------------------------------
+// circuit IR + OpenQASM 2 reader
+// ------------------------------------------------------------------------------------------------
+struct Op {
+    enum Kind { Unitary, Measure, Barrier, Reset } kind = Unitary;
+    std::string name;          // gate name as written
+    std::vector<int> qubits;   // operands in the order written (controls first for c* gates)
+    std::vector<double> params;
+};
+
+struct Circuit {
+    std::string name;
+    int nQubits = 0;
+    int nClbits = 0;
+    std::vector<Op> ops; // one entry per statement, like qc::QuantumComputation::getNops()
+    [[nodiscard]] std::size_t nOps() const { return ops.size(); }
+};
+
+class QasmError : public std::runtime_error {
+public:
+    using std::runtime_error::runtime_error;
+};
+
+namespace detail {
+
+// arithmetic of gate parameters: + - * / ^, unary minus, parentheses, pi, sin cos tan exp ln sqrt
+class Expr {
+public:
+    explicit Expr(const std::string& s) : s_(s) {}
+    double parse() {
+        const double v = sum();
+        skip();
+        if (pos_ != s_.size()) throw QasmError("cannot parse parameter '" + s_ + "'");
+        return v;
+    }
+
+private:
+    void skip() {
+        while (pos_ < s_.size() && std::isspace(static_cast<unsigned char>(s_[pos_]))) ++pos_;
+    }
+    bool eat(char c) {
+        skip();
+        if (pos_ < s_.size() && s_[pos_] == c) {
+            ++pos_;
+            return true;
+        }
+        return false;
+    }
+    double sum() {
+        double v = product();
+        for (;;) {
+            if (eat('+')) v += product();
+            else if (eat('-')) v -= product();
+            else return v;
+        }
+    }
+    double product() {
+        double v = unary();
+        for (;;) {
+            if (eat('*')) v *= unary();
+            else if (eat('/')) v /= unary();
+            else return v;
+        }
+    }
+    double unary() {
+        if (eat('-')) return -unary();
+        if (eat('+')) return unary();
+        const double base = primary();
+        if (eat('^')) return std::pow(base, unary());
+        return base;
+    }
+    double primary() {
+        skip();
+        if (eat('(')) {
+            const double v = sum();
+            if (!eat(')')) throw QasmError("missing ')' in parameter '" + s_ + "'");
+            return v;
+        }
+        if (pos_ < s_.size() && (std::isdigit(static_cast<unsigned char>(s_[pos_])) || s_[pos_] == '.')) {
+            std::size_t used = 0;
+            const double v = std::stod(s_.substr(pos_), &used);
+            pos_ += used;
+            return v;
+        }
+        std::string id;
+        while (pos_ < s_.size() && (std::isalnum(static_cast<unsigned char>(s_[pos_])) || s_[pos_] == '_')) id += s_[pos_++];
+        if (id == "pi") return M_PI;
+        if (id.empty()) throw QasmError("cannot parse parameter '" + s_ + "'");
+        if (!eat('(')) throw QasmError("unknown identifier '" + id + "' in parameter");
+        const double a = sum();
+        if (!eat(')')) throw QasmError("missing ')' in parameter '" + s_ + "'");
+        if (id == "sin") return std::sin(a);
+        if (id == "cos") return std::cos(a);
+        if (id == "tan") return std::tan(a);
+        if (id == "exp") return std::exp(a);
+        if (id == "ln") return std::log(a);
+        if (id == "sqrt") return std::sqrt(a);
+        throw QasmError("unknown function '" + id + "'");
+    }
+    const std::string& s_;
+    std::size_t pos_ = 0;
+};
+
+inline std::string trim(const std::string& s) {
+    std::size_t a = 0, b = s.size();
+    while (a < b && std::isspace(static_cast<unsigned char>(s[a]))) ++a;
+    while (b > a && std::isspace(static_cast<unsigned char>(s[b - 1]))) --b;
+    return s.substr(a, b - a);
+}
+
+inline std::vector<std::string> splitTop(const std::string& s, char sep) { // split outside parentheses
+    std::vector<std::string> out;
+    int depth = 0;
+    std::string cur;
+    for (char c : s) {
+        if (c == '(') ++depth;
+        if (c == ')') --depth;
+        if (c == sep && depth == 0) {
+            out.push_back(trim(cur));
+            cur.clear();
+        } else {
+            cur += c;
+        }
+    }
+    if (!trim(cur).empty()) out.push_back(trim(cur));
+    return out;
+}
+
+} // namespace detail
+
+inline Circuit parseQasm(std::istream& in, const std::string& name) {
+    Circuit c;
+    c.name = name;
+    std::string text, line;
+    while (std::getline(in, line)) {
+        const auto cut = line.find("//");
+        text += (cut == std::string::npos ? line : line.substr(0, cut));
+        text += '\n';
+    }
+    if (text.find('{') != std::string::npos) throw QasmError("gate definitions / blocks are not supported by the standalone reader");
+    struct Reg {
+        int first, size;
+    };
+    std::map<std::string, Reg> qregs, cregs;
+    // operand "q[3]" -> {3 + first}; "q" -> the whole register
+    auto operand = [&](const std::string& tok, const std::map<std::string, Reg>& regs) {
+        std::vector<int> out;
+        const auto lb = tok.find('[');
+        const std::string reg = detail::trim(tok.substr(0, lb));
+        const auto it = regs.find(reg);
+        if (it == regs.end()) throw QasmError("unknown register '" + reg + "'");
+        if (lb == std::string::npos) {
+            for (int i = 0; i < it->second.size; ++i) out.push_back(it->second.first + i);
+        } else {
+            const int idx = std::stoi(tok.substr(lb + 1));
+            if (idx < 0 || idx >= it->second.size) throw QasmError("index out of range in '" + tok + "'");
+            out.push_back(it->second.first + idx);
+        }
+        return out;
+    };
+    for (const std::string& raw : detail::splitTop(text, ';')) {
+        const std::string st = detail::trim(raw);
+        if (st.empty()) continue;
+        std::size_t p = 0;
+        while (p < st.size() && (std::isalnum(static_cast<unsigned char>(st[p])) || st[p] == '_')) ++p;
+        const std::string head = st.substr(0, p);
+        std::string rest = detail::trim(st.substr(p));
+        if (head == "OPENQASM" || head == "include") continue;
+        if (head == "qreg" || head == "creg") {
+            const auto lb = rest.find('['), rb = rest.find(']');
+            if (lb == std::string::npos || rb == std::string::npos) throw QasmError("bad register declaration '" + st + "'");
+            const std::string reg = detail::trim(rest.substr(0, lb));
+            const int size = std::stoi(rest.substr(lb + 1, rb - lb - 1));
+            if (head == "qreg") {
+                qregs[reg] = {c.nQubits, size};
+                c.nQubits += size;
+            } else {
+                cregs[reg] = {c.nClbits, size};
+                c.nClbits += size;
+            }
+            continue;
+        }
+        Op op;
+        op.name = head;
+        if (head == "measure") {
+            op.kind = Op::Measure;
+            const auto arrow = rest.find("->");
+            if (arrow == std::string::npos) throw QasmError("measure without '->'");
+            op.qubits = operand(detail::trim(rest.substr(0, arrow)), qregs);
+            c.ops.push_back(op);
+            continue;
+        }
+        if (head == "barrier" || head == "reset") {
+            op.kind = head == "barrier" ? Op::Barrier : Op::Reset;
+            for (const auto& tok : detail::splitTop(rest, ',')) {
+                for (int q : operand(tok, qregs)) op.qubits.push_back(q);
+            }
+            c.ops.push_back(op);
+            continue;
+        }
+        if (!rest.empty() && rest[0] == '(') {
+            int depth = 0;
+            std::size_t close = 0;
+            for (; close < rest.size(); ++close) {
+                if (rest[close] == '(') ++depth;
+                if (rest[close] == ')' && --depth == 0) break;
+            }
+            if (close == rest.size()) throw QasmError("missing ')' in '" + st + "'");
+            for (const auto& e : detail::splitTop(rest.substr(1, close - 1), ',')) op.params.push_back(detail::Expr(e).parse());
+            rest = detail::trim(rest.substr(close + 1));
+        }
+        // operands; a whole-register operand broadcasts the gate (one Op per element, one statement)
+        std::vector<std::vector<int>> args;
+        std::size_t broadcast = 1;
+        for (const auto& tok : detail::splitTop(rest, ',')) {
+            args.push_back(operand(tok, qregs));
+            if (args.back().size() > 1) broadcast = args.back().size();
+        }
+        if (args.empty()) throw QasmError("gate without operands: '" + st + "'");
+        for (std::size_t b = 0; b < broadcast; ++b) {
+            Op one = op;
+            for (const auto& a : args) one.qubits.push_back(a.size() > 1 ? a[b] : a[0]);
+            c.ops.push_back(one);
+        }
+    }
+    if (c.nQubits == 0) throw QasmError("no qreg declared");
+    return c;
+}
+
+inline Circuit parseQasmFile(const std::string& path) {
+    std::ifstream in(path);
+    if (!in) throw QasmError("cannot open " + path);
+    std::string name = path;
+    const auto slash = name.find_last_of('/');
+    if (slash != std::string::npos) name = name.substr(slash + 1);
+    const auto dot = name.find_last_of('.');
+    if (dot != std::string::npos) name = name.substr(0, dot);
+    return parseQasm(in, name);
+}
+
+// ------------------------------------------------------------------------------------------------
+// gate matrices (reference include/dd/GateMatrixDefinitions.hpp)
+// ------------------------------------------------------------------------------------------------
+// A dense block on a sorted set of qubits: bit i of a row / column index belongs to qubits[i].
+struct Block {
+    std::vector<int> qubits;
+    std::vector<cplx> m; // row-major, dim x dim, dim = 2^qubits.size()
+    [[nodiscard]] std::size_t dim() const { return std::size_t{1} << qubits.size(); }
+};
+
+namespace detail {
+
+using M2 = std::array<cplx, 4>;
+using M4 = std::array<cplx, 16>;
+
+inline M2 u3(double theta, double phi, double lambda) {
+    return {cplx(std::cos(theta / 2), 0.0), cplx(-std::cos(lambda) * std::sin(theta / 2), -std::sin(lambda) * std::sin(theta / 2)),
+            cplx(std::cos(phi) * std::sin(theta / 2), std::sin(phi) * std::sin(theta / 2)),
+            cplx(std::cos(lambda + phi) * std::cos(theta / 2), std::sin(lambda + phi) * std::cos(theta / 2))};
+}
+
+inline bool oneQubitMatrix(const std::string& g, const std::vector<double>& p, M2& out) {
+    const double s = M_SQRT1_2;
+    const cplx i(0, 1);
+    auto need = [&](std::size_t n) {
+        if (p.size() != n) throw QasmError("gate " + g + " takes " + std::to_string(n) + " parameter(s)");
+    };
+    if (g == "id" || g == "i") out = {1, 0, 0, 1};
+    else if (g == "x") out = {0, 1, 1, 0};
+    else if (g == "y") out = {0, -i, i, 0};
+    else if (g == "z") out = {1, 0, 0, -1};
+    else if (g == "h") out = {s, s, s, -s};
+    else if (g == "s") out = {1, 0, 0, i};
+    else if (g == "sdg") out = {1, 0, 0, -i};
+    else if (g == "t") out = {1, 0, 0, cplx(s, s)};
+    else if (g == "tdg") out = {1, 0, 0, cplx(s, -s)};
+    else if (g == "sx") out = {cplx(0.5, 0.5), cplx(0.5, -0.5), cplx(0.5, -0.5), cplx(0.5, 0.5)};
+    else if (g == "sxdg") out = {cplx(0.5, -0.5), cplx(0.5, 0.5), cplx(0.5, 0.5), cplx(0.5, -0.5)};
+    else if (g == "rx") { need(1); out = {cplx(std::cos(p[0] / 2), 0), cplx(0, -std::sin(p[0] / 2)), cplx(0, -std::sin(p[0] / 2)), cplx(std::cos(p[0] / 2), 0)}; }
+    else if (g == "ry") { need(1); out = {std::cos(p[0] / 2), -std::sin(p[0] / 2), std::sin(p[0] / 2), std::cos(p[0] / 2)}; }
+    else if (g == "rz") { need(1); out = {cplx(std::cos(p[0] / 2), -std::sin(p[0] / 2)), 0, 0, cplx(std::cos(p[0] / 2), std::sin(p[0] / 2))}; }
+    else if (g == "p" || g == "u1" || g == "phase") { need(1); out = {1, 0, 0, cplx(std::cos(p[0]), std::sin(p[0]))}; }
+    else if (g == "u2") { need(2); out = u3(M_PI / 2, p[0], p[1]); out[0] = s; }
+    else if (g == "u3" || g == "u" || g == "U") { need(3); out = u3(p[0], p[1], p[2]); }
+    else return false;
+    return true;
+}
+
+// 4x4 matrices: index = 2 * (bit of the first listed qubit) + (bit of the second)
+inline bool twoQubitMatrix(const std::string& g, const std::vector<double>& p, M4& out) {
+    const cplx i(0, 1);
+    out.fill(0);
+    auto rot = [&](double& c, double& s) {
+        if (p.size() != 1) throw QasmError("gate " + g + " takes 1 parameter");
+        c = std::cos(p[0] / 2);
+        s = std::sin(p[0] / 2);
+    };
+    double c = 0, s = 0;
+    if (g == "swap") { out[0] = out[6] = out[9] = out[15] = 1; }
+    else if (g == "iswap") { out[0] = out[15] = 1; out[6] = out[9] = i; }
+    else if (g == "dcx") { out[0] = 1; out[7] = 1; out[9] = 1; out[14] = 1; }
+    else if (g == "rzz") { rot(c, s); out[0] = out[15] = cplx(c, -s); out[5] = out[10] = cplx(c, s); }
+    else if (g == "rxx") { rot(c, s); out[0] = out[5] = out[10] = out[15] = c; out[3] = out[6] = out[9] = out[12] = cplx(0, -s); }
+    else if (g == "ryy") { rot(c, s); out[0] = out[5] = out[10] = out[15] = c; out[3] = out[12] = cplx(0, s); out[6] = out[9] = cplx(0, -s); }
+    else if (g == "rzx") { rot(c, s); out[0] = out[5] = out[10] = out[15] = c; out[1] = out[4] = cplx(0, -s); out[11] = out[14] = cplx(0, s); }
+    else return false;
+    return true;
+}
+
+} // namespace detail
+
+// The operation as a dense block on its own qubits.  Leading 'c's of the name are controls
+// (cx, ccx, cswap, cu3, ...), the rest is a one- or two-target base gate.
+inline Block blockOf(const Op& op) {
+    std::string base = op.name;
+    if (base == "CX") base = "cx";
+    if (base == "cnot") base = "cx";
+    if (base == "toffoli") base = "ccx";
+    if (base == "fredkin") base = "cswap";
+    detail::M2 m2{};
+    detail::M4 m4{};
+    int nControls = 0;
+    int nTargets = 0;
+    for (;;) {
+        if (detail::oneQubitMatrix(base, op.params, m2)) {
+            nTargets = 1;
+            break;
+        }
+        if (detail::twoQubitMatrix(base, op.params, m4)) {
+            nTargets = 2;
+            break;
+        }
+        if (base.size() > 1 && base[0] == 'c') {
+            base = base.substr(1);
+            ++nControls;
+            continue;
+        }
+        throw QasmError("unsupported gate '" + op.name + "'");
+    }
+    if (static_cast<int>(op.qubits.size()) != nControls + nTargets) {
+        throw QasmError("gate " + op.name + " takes " + std::to_string(nControls + nTargets) + " qubit(s)");
+    }
+    Block b;
+    b.qubits = op.qubits;
+    std::sort(b.qubits.begin(), b.qubits.end());
+    if (std::adjacent_find(b.qubits.begin(), b.qubits.end()) != b.qubits.end()) throw QasmError("gate " + op.name + " repeats a qubit");
+    auto pos = [&](int q) { return static_cast<int>(std::lower_bound(b.qubits.begin(), b.qubits.end(), q) - b.qubits.begin()); };
+    const std::size_t dim = b.dim();
+    b.m.assign(dim * dim, cplx(0, 0));
+    std::size_t controlMask = 0;
+    for (int k = 0; k < nControls; ++k) controlMask |= std::size_t{1} << pos(op.qubits[static_cast<std::size_t>(k)]);
+    const int t0 = pos(op.qubits[static_cast<std::size_t>(nControls)]);
+    const int t1 = nTargets == 2 ? pos(op.qubits[static_cast<std::size_t>(nControls) + 1]) : -1;
+    for (std::size_t r = 0; r < dim; ++r) {
+        for (std::size_t c = 0; c < dim; ++c) {
+            std::size_t targetMask = std::size_t{1} << t0;
+            if (t1 >= 0) targetMask |= std::size_t{1} << t1;
+            if (((r ^ c) & ~targetMask) != 0) continue; // controls (and nothing else) are untouched
+            if ((r & controlMask) != controlMask) {
+                if (r == c) b.m[r * dim + c] = 1.0;
+                continue;
+            }
+            if (nTargets == 1) {
+                b.m[r * dim + c] = m2[2 * ((r >> t0) & 1) + ((c >> t0) & 1)];
+            } else {
+                const std::size_t ri = 2 * ((r >> t0) & 1) + ((r >> t1) & 1);
+                const std::size_t ci = 2 * ((c >> t0) & 1) + ((c >> t1) & 1);
+                b.m[r * dim + c] = m4[4 * ri + ci];
+            }
+        }
+    }
+    return b;
+}
+
+// the block on a larger sorted qubit set (identity on the added qubits)
+inline Block expand(const Block& b, const std::vector<int>& onto) {
+    if (b.qubits == onto) return b;
+    Block out;
+    out.qubits = onto;
+    const std::size_t dim = out.dim();
+    out.m.assign(dim * dim, cplx(0, 0));
+    std::vector<int> at; // position of each of b's qubits inside `onto`
+    for (int q : b.qubits) at.push_back(static_cast<int>(std::lower_bound(onto.begin(), onto.end(), q) - onto.begin()));
+    std::size_t own = 0;
+    for (int p : at) own |= std::size_t{1} << p;
+    auto gatherBits = [&](std::size_t x) {
+        std::size_t v = 0;
+        for (std::size_t i = 0; i < at.size(); ++i) v |= ((x >> at[i]) & 1) << i;
+        return v;
+    };
+    const std::size_t bd = b.dim();
+    for (std::size_t r = 0; r < dim; ++r) {
+        for (std::size_t c = 0; c < dim; ++c) {
+            if (((r ^ c) & ~own) != 0) continue;
+            out.m[r * dim + c] = b.m[gatherBits(r) * bd + gatherBits(c)];
+        }
+    }
+    return out;
+}
+
+// next * current (next acts after current)
+inline Block multiply(const Block& next, const Block& current) {
+    std::vector<int> all;
+    std::set_union(next.qubits.begin(), next.qubits.end(), current.qubits.begin(), current.qubits.end(), std::back_inserter(all));
+    const Block a = expand(next, all), b = expand(current, all);
+    Block out;
+    out.qubits = all;
+    const std::size_t dim = out.dim();
+    out.m.assign(dim * dim, cplx(0, 0));
+    for (std::size_t r = 0; r < dim; ++r) {
+        for (std::size_t k = 0; k < dim; ++k) {
+            const cplx x = a.m[r * dim + k];
+            if (x == cplx(0, 0)) continue;
+            for (std::size_t c = 0; c < dim; ++c) out.m[r * dim + c] += x * b.m[k * dim + c];
+        }
+    }
+    return out;
+}
+
+// qubits (positions in b.qubits) on which the block is not diagonal
+inline int nonDiagonalCount(const Block& b) {
+    const std::size_t dim = b.dim();
+    std::size_t mask = 0;
+    for (std::size_t r = 0; r < dim; ++r) {
+        for (std::size_t c = 0; c < dim; ++c) {
+            if (b.m[r * dim + c] != cplx(0, 0)) mask |= r ^ c;
+        }
+    }
+    return __builtin_popcountll(mask);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense block -> flat matrix DD (full depth, identity levels explicit, normalised so that equal
+// sub-blocks share nodes: a Kronecker product gets one node per level)
+// ------------------------------------------------------------------------------------------------
+class GateDDBuilder {
+public:
+    explicit GateDDBuilder(int nQubits) : n_(nQubits) {}
+
+    FlatMatDD build(const Block& b) {
+        out_ = FlatMatDD{};
+        out_.n_qubits = n_;
+        unique_.clear();
+        memo_.clear();
+        ident_.assign(static_cast<std::size_t>(n_) + 1, FDD_TERMINAL - 1);
+        block_ = &b;
+        posOf_.assign(static_cast<std::size_t>(n_), -1);
+        for (std::size_t i = 0; i < b.qubits.size(); ++i) {
+            if (b.qubits[i] < 0 || b.qubits[i] >= n_) throw std::runtime_error("block qubit out of range");
+            posOf_[static_cast<std::size_t>(b.qubits[i])] = static_cast<int>(i);
+        }
+        const Edge root = make(n_ - 1, 0, 0);
+        if (root.w == cplx(0, 0)) throw std::runtime_error("zero matrix");
+        out_.root = root.node;
+        out_.root_weight[0] = root.w.real();
+        out_.root_weight[1] = root.w.imag();
+        return std::move(out_);
+    }
+
+private:
+    struct Edge {
+        int32_t node = FDD_TERMINAL;
+        cplx w{0, 0};
+    };
+    static int64_t grid(double x) { return static_cast<int64_t>(std::llround(x * 70368744177664.0)); } // 2^-46 steps
+    int32_t identChain(int lv) {
+        if (lv < 0) return FDD_TERMINAL;
+        int32_t& slot = ident_[static_cast<std::size_t>(lv)];
+        if (slot == FDD_TERMINAL - 1) {
+            const int32_t below = identChain(lv - 1);
+            slot = addNode(lv, {Edge{below, 1.0}, Edge{}, Edge{}, Edge{below, 1.0}}, lv == 0);
+        }
+        return slot;
+    }
+    int32_t addNode(int lv, const std::array<Edge, 4>& e, bool leafLevel) {
+        std::array<int64_t, 13> key{};
+        key[0] = lv;
+        for (int k = 0; k < 4; ++k) {
+            key[1 + 3 * k] = e[k].w == cplx(0, 0) ? -7 : e[k].node;
+            key[2 + 3 * k] = grid(e[k].w.real());
+            key[3 + 3 * k] = grid(e[k].w.imag());
+        }
+        const auto it = unique_.find(key);
+        if (it != unique_.end()) return it->second;
+        const auto id = static_cast<int32_t>(out_.level.size());
+        out_.level.push_back(lv);
+        for (int k = 0; k < 4; ++k) {
+            const bool zero = e[k].w == cplx(0, 0);
+            out_.child.push_back(zero || leafLevel ? FDD_TERMINAL : e[k].node);
+            out_.weight.push_back(zero ? 0.0 : e[k].w.real());
+            out_.weight.push_back(zero ? 0.0 : e[k].w.imag());
+        }
+        unique_.emplace(key, id);
+        return id;
+    }
+    // sub-matrix with the block bits of all levels above `lv` fixed to (r, c)
+    Edge make(int lv, std::size_t r, std::size_t c) {
+        const Block& b = *block_;
+        const int lowest = b.qubits.front();
+        if (lv < lowest) { // identity below the lowest block qubit, the entry rides on the edge
+            const cplx v = b.m[r * b.dim() + c];
+            if (v == cplx(0, 0)) return Edge{};
+            return Edge{identChain(lv), v};
+        }
+        const uint64_t memoKey = (static_cast<uint64_t>(lv) << 40) | (static_cast<uint64_t>(r) << 20) | static_cast<uint64_t>(c);
+        const auto hit = memo_.find(memoKey);
+        if (hit != memo_.end()) return hit->second;
+        std::array<Edge, 4> e{};
+        const int p = posOf_[static_cast<std::size_t>(lv)];
+        if (p >= 0) {
+            for (std::size_t rb = 0; rb < 2; ++rb) {
+                for (std::size_t cb = 0; cb < 2; ++cb) e[2 * rb + cb] = make(lv - 1, r | (rb << p), c | (cb << p));
+            }
+        } else {
+            e[0] = e[3] = make(lv - 1, r, c);
+        }
+        // normalise: the largest weight (first on ties) becomes 1 and moves to the incoming edge
+        int top = -1;
+        double best = 0.0;
+        for (int k = 0; k < 4; ++k) {
+            const double mag = std::norm(e[k].w);
+            if (mag > best * (1.0 + 1e-12)) {
+                best = mag;
+                top = k;
+            }
+        }
+        Edge res;
+        if (top >= 0) {
+            const cplx f = e[top].w;
+            for (int k = 0; k < 4; ++k) {
+                if (e[k].w == cplx(0, 0)) continue;
+                if (k == top || e[k].w == f) {
+                    e[k].w = cplx(1, 0); // x / x is not exactly 1 in complex arithmetic; identity levels must stay exact
+                } else {
+                    cplx q = e[k].w / f;
+                    if (std::abs(q.real()) < 1e-15) q.real(0.0); // rounding dust of the division, far below the DD tolerance
+                    if (std::abs(q.imag()) < 1e-15) q.imag(0.0);
+                    e[k].w = q;
+                }
+            }
+            res.node = addNode(lv, e, lv == 0);
+            res.w = f;
+        }
+        memo_.emplace(memoKey, res);
+        return res;
+    }
+
+    struct KeyHash {
+        std::size_t operator()(const std::array<int64_t, 13>& k) const {
+            uint64_t h = 1469598103934665603ULL;
+            for (int64_t v : k) {
+                h ^= static_cast<uint64_t>(v);
+                h *= 1099511628211ULL;
+            }
+            return static_cast<std::size_t>(h);
+        }
+    };
+    int n_;
+    FlatMatDD out_;
+    const Block* block_ = nullptr;
+    std::vector<int> posOf_;
+    std::vector<int32_t> ident_;
+    std::unordered_map<std::array<int64_t, 13>, int32_t, KeyHash> unique_;
+    std::unordered_map<uint64_t, Edge> memo_;
+};
+
+// |0...0> as a vector DD: one node per level, weight 1 on the 0-successor
+inline FlatVecDD zeroStateDD(int nQubits) {
+    FlatVecDD v;
+    v.n_qubits = nQubits;
+    v.root = 0;
+    v.root_weight[0] = 1.0;
+    for (int i = 0; i < nQubits; ++i) {
+        v.level.push_back(nQubits - 1 - i);
+        v.child.push_back(i + 1 < nQubits ? i + 1 : FDD_TERMINAL);
+        v.child.push_back(FDD_TERMINAL);
+        v.weight.insert(v.weight.end(), {1.0, 0.0, 0.0, 0.0});
+    }
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the simulator
+// ------------------------------------------------------------------------------------------------
+struct FusionPolicy {
+    int maxBlockQubits = 5;  // qubits of one fused block (diagonal ones included)
+    int maxNonDiagonal = 4;  // of which non-diagonal: sizes the kernel's tile (16 segments: the tensor-core path)
+};
+
+class FlatStartSimulator {
+public:
+    FlatStartSimulator(Circuit circuit, ArrayBackend* backend) : qc_(std::move(circuit)), backend_(backend) {}
+
+    // knobs with the names of the reference simulator where they still mean something
+    unsigned fuse = 0;    // 0: one launch per gate; >= 1: dense-block fusion
+    bool verbose = true;
+    FusionPolicy policy;
+
+    // results
+    std::size_t unitaryOps = 0;
+    std::size_t launches = 0;
+    double arrayPhaseTime = 0.0;   // seconds, wall clock around the launches (synchronised at the end)
+    double gateMergingTime = 0.0;  // seconds spent fusing and building gate DDs
+    double kernelMsTotal = 0.0;    // with per-launch timing on
+    std::vector<double> timeRecord2;
+
+    void simulate() {
+        const auto t0 = std::chrono::steady_clock::now();
+        backend_->convert(zeroStateDD(qc_.nQubits));
+        GateDDBuilder builder(qc_.nQubits);
+        // Open blocks have pairwise disjoint qubit sets, so they commute: an operation only has to come after
+        // the blocks it shares a qubit with, and the others stay open for later operations (a layer of
+        // one-qubit gates over the whole register ends up in ceil(n / maxNonDiagonal) blocks instead of n).
+        std::vector<Open> open;
+        std::size_t opIndex = 0;
+        auto emit = [&](const Open& o) {
+            const auto m0 = std::chrono::steady_clock::now();
+            const FlatMatDD gate = builder.build(o.block);
+            gateMergingTime += seconds(m0);
+            const auto a0 = std::chrono::steady_clock::now();
+            backend_->apply(gate, o.count);
+            kernelMsTotal += backend_->lastKernelMs();
+            timeRecord2.push_back(seconds(a0));
+            ++launches;
+        };
+        for (const Op& op : qc_.ops) {
+            if (verbose && opIndex % 100 == 0) std::printf("[Instruction Count]  %zu\n", opIndex);
+            ++opIndex;
+            if (op.kind == Op::Measure || op.kind == Op::Barrier) continue; // skipped like the reference (src/SwitchSimulator.cpp:108-113)
+            if (op.kind == Op::Reset) throw std::runtime_error("reset is not supported");
+            ++unitaryOps;
+            const auto m0 = std::chrono::steady_clock::now();
+            Open next{blockOf(op), 1};
+            if (fuse == 0) {
+                gateMergingTime += seconds(m0);
+                emit(next);
+                continue;
+            }
+            std::vector<std::size_t> touching;
+            std::vector<int> all = next.block.qubits;
+            for (std::size_t i = 0; i < open.size(); ++i) {
+                std::vector<int> common;
+                std::set_intersection(open[i].block.qubits.begin(), open[i].block.qubits.end(), next.block.qubits.begin(), next.block.qubits.end(),
+                                      std::back_inserter(common));
+                if (common.empty()) continue;
+                touching.push_back(i);
+                std::vector<int> merged;
+                std::set_union(all.begin(), all.end(), open[i].block.qubits.begin(), open[i].block.qubits.end(), std::back_inserter(merged));
+                all.swap(merged);
+            }
+            bool fused = false;
+            if (static_cast<int>(all.size()) <= policy.maxBlockQubits) {
+                Open candidate = next;
+                for (std::size_t i : touching) { // the open blocks commute with each other; the new operation comes last
+                    candidate.block = multiply(candidate.block, open[i].block);
+                    candidate.count += open[i].count;
+                }
+                if (nonDiagonalCount(candidate.block) <= policy.maxNonDiagonal) {
+                    next = std::move(candidate);
+                    fused = true;
+                }
+            }
+            gateMergingTime += seconds(m0);
+            if (!fused) {
+                // the touching blocks have to run now; blocks on disjoint qubits may share their launch
+                // (a Kronecker product) as long as the policy holds
+                std::vector<Open> leaving;
+                for (std::size_t i : touching) leaving.push_back(std::move(open[i]));
+                for (Open& o : pack(leaving)) emit(o);
+            }
+            for (auto it = touching.rbegin(); it != touching.rend(); ++it) open.erase(open.begin() + static_cast<std::ptrdiff_t>(*it));
+            open.push_back(std::move(next));
+        }
+        for (Open& o : pack(open)) emit(o);
+        backend_->synchronize();
+        arrayPhaseTime = seconds(t0) - gateMergingTime;
+        if (verbose) {
+            std::printf("Gate merging time: %g\n", gateMergingTime);
+            std::printf("Merged Gate Number: %zu\n", launches);
+        }
+    }
+
+    [[nodiscard]] const Circuit& circuit() const { return qc_; }
+    void getVector(std::vector<double>& re, std::vector<double>& im) {
+        re.resize(std::size_t{1} << qc_.nQubits);
+        im.resize(re.size());
+        backend_->getState(re.data(), im.data());
+    }
+
+private:
+    struct Open {
+        Block block;
+        int count = 0;
+    };
+    // first-fit packing of pairwise disjoint blocks into as few launches as the policy allows
+    std::vector<Open> pack(std::vector<Open>& blocks) const {
+        std::vector<Open> out;
+        for (Open& b : blocks) {
+            bool placed = false;
+            for (Open& o : out) {
+                std::vector<int> all;
+                std::set_union(o.block.qubits.begin(), o.block.qubits.end(), b.block.qubits.begin(), b.block.qubits.end(), std::back_inserter(all));
+                if (static_cast<int>(all.size()) > policy.maxBlockQubits) continue;
+                if (nonDiagonalCount(o.block) + nonDiagonalCount(b.block) > policy.maxNonDiagonal) continue;
+                o.block = multiply(b.block, o.block);
+                o.count += b.count;
+                placed = true;
+                break;
+            }
+            if (!placed) out.push_back(std::move(b));
+        }
+        return out;
+    }
+    static double seconds(std::chrono::steady_clock::time_point since) {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - since).count();
+    }
+    Circuit qc_;
+    ArrayBackend* backend_;
+};
+
+} // namespace fddb200::standalone

@@ -96,10 +96,10 @@ int fdd_n_qubits(const fdd_ctx* ctx);
 int fdd_n_local_qubits(const fdd_ctx* ctx);
 int fdd_synchronize(fdd_ctx* ctx);
 /* Tunables for experiments: "dmavm_variant" (2 tile kernel where the gate allows, 1 / 0 walk kernels, 9 chunk kernel),
- * "warps_per_cta", "ctas_per_sm", "prefetch", "tile_mode", "dense_slots", "dmma", "flat_table", "exchange_unroll", "exchange_ctas_per_sm". */
+ * "warps_per_cta", "ctas_per_sm", "prefetch", "tile_mode", "dense_slots", "dmma", "flat_table", "pdl", "context_table", "exchange_unroll", "exchange_ctas_per_sm". */
 int fdd_set_option(fdd_ctx* ctx, const char* key, long value);
 /* Reads a tunable back, or a launch counter: "launches", "tensor_core_launches" (DMAVM launches that ran the
- * FP64 tensor-core path), "flat_table_launches", "exchanges". */
+ * FP64 tensor-core path), "flat_table_launches", "context_table_launches", "exchanges". */
 int fdd_get_option(const fdd_ctx* ctx, const char* key, long* value);
 
 /* ---- multi-GPU (one process per GPU) ----------------------------------

@@ -307,6 +307,8 @@ TENSOR_CORE_SHAPES = [
     (15, [12, 8, 6, 10, 14], "ctrl"),   # control on qubit 12, dense on four others: the block differs from tile to tile
     (15, [13, 7, 9, 11], "ctrl"),       # same with an 8-segment tile
     (14, [6, 8, 10, 12], "half"),       # eight sources per output segment inside a 16-segment tile
+    (16, [12, 7, 14, 6, 9, 11], "ctrl3"),  # three controls (one of them a fill bit of the warp tile): 8 context blocks
+    (17, [5, 16, 8, 10, 12, 14], "ctrl2"),  # controls on the lowest and the highest segment bit
 ]
 
 
@@ -317,8 +319,9 @@ def test_tensor_core_path_vs_numpy_and_fma_path(n, targets, kind):
     k = len(targets)
     if kind == "dense":
         u = B.random_unitary(k, rng)
-    elif kind == "ctrl":
-        u = B.controlled(B.random_unitary(k - 1, rng), 1)
+    elif kind.startswith("ctrl"):
+        nc = int(kind[4:] or 1)
+        u = B.controlled(B.random_unitary(k - nc, rng), nc)
     else:
         u = np.kron(B.random_unitary(k - 1, rng), np.array([[0.0, 1.0], [1.0, 0.0]]))  # X on the lowest target
     gate = B.gate_dd(n, targets, u)
@@ -333,6 +336,16 @@ def test_tensor_core_path_vs_numpy_and_fma_path(n, targets, kind):
             ctx.apply(gate)  # both ping-pong directions
             out[dmma] = ctx.get_state()
             assert ctx.get_option("tensor_core_launches") == (2 if dmma else 0)
+            assert ctx.get_option("context_table_launches") == (2 if dmma else 0)
+    if True:  # the walk inside the launch (no context table) gives the same state
+        with Context(n) as ctx:
+            ctx.set_option("context_table", 0)
+            ctx.set_state(yr, yi)
+            ctx.apply(gate)
+            ctx.apply(gate)
+            walked = ctx.get_state()
+            assert ctx.get_option("tensor_core_launches") == 2 and ctx.get_option("context_table_launches") == 0
+        assert G.max_amp_err(out[1][0], out[1][1], walked[0], walked[1]) == 0.0
     ref2 = B.apply_dense(n, targets, u, ref)
     for dmma in (1, 0):
         assert np.max(np.abs((out[dmma][0] + 1j * out[dmma][1]) - ref2)) < AMP_TOL

@@ -1,0 +1,75 @@
+"""GPU tests of the standalone front end (build/flatdd_gpu_standalone: own OpenQASM reader, dense-block
+fusion, flat start; no reference code at build or run time): whole circuits on the device against the
+final states of the unmodified reference."""
+import json
+import subprocess
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from tests import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+ROOT = Path(__file__).resolve().parents[1]
+CLI = ROOT / "build" / "flatdd_gpu_standalone"
+
+SMALL = [("tiny_n3", "tiny_n3_f0"), ("small_n5", "small_n5_f0"), ("mix_n7", "mix_n7_f0"), ("qft_n8", "qft_n8_f0"), ("ghz_n6", "ghz_n6_f0"),
+         ("mix_n10", "mix_n10_f0"), ("brick_n11", "brick_n11_f1"), ("mix_n12", "mix_n12_f0")]
+
+
+def run(circuit: Path, fuse: int, extra=()):
+    with tempfile.TemporaryDirectory() as tmp:
+        cwd = Path(tmp) / "build" / "apps"
+        cwd.mkdir(parents=True)
+        (Path(tmp) / "log" / "results" / "time").mkdir(parents=True)
+        state = Path(tmp) / "state.bin"
+        out = subprocess.run([str(CLI), "--file", str(circuit), "--fuse", str(fuse), "--bin", str(state), "--quiet", *extra],
+                             cwd=cwd, capture_output=True, text=True, check=True).stdout
+        raw = np.fromfile(state, dtype="<f8")
+    full = json.loads(out[out.rindex("\n{\n") + 1:])
+    return full, raw[: raw.size // 2], raw[raw.size // 2:]
+
+
+@pytest.mark.skipif(not CLI.exists(), reason="build/flatdd_gpu_standalone not built")
+@pytest.mark.parametrize("fuse", [0, 1])
+@pytest.mark.parametrize("name,golden", SMALL)
+def test_standalone_final_state(name, golden, fuse):
+    full, re, im = run(ROOT / "tests" / "circuits" / f"{name}.qasm", fuse)
+    fr, fi = G.final_state(golden)
+    assert G.max_amp_err(re, im, fr, fi) < 1e-10
+    assert 1.0 - G.fidelity(re, im, fr, fi) < 1e-10
+    stats = full["statistics"]
+    assert stats["gpu_kernel_launches"] >= stats["array_phase_launches"] + 1 and stats["applied_gates"] == G.manifest(golden)["n_ops"]
+
+
+TRAVEL = [c for c in G.cases(G.TRAVEL)]
+
+
+@pytest.mark.skipif(not CLI.exists(), reason="build/flatdd_gpu_standalone not built")
+@pytest.mark.parametrize("case", TRAVEL)
+def test_standalone_on_reference_circuits(case):
+    """The reference's own circuits (golden data written by the compiled reference, oracle/_ref/golden)."""
+    m = G.manifest(case, G.TRAVEL)
+    circuit = ROOT / "oracle" / "_ref" / "circuits" / m["circuit"]
+    if not circuit.exists():
+        pytest.skip(f"{circuit} not present")
+    full, re, im = run(circuit, 1, extra=("--time-gates",))
+    if (G.TRAVEL / case / "final_re.f64").exists():
+        fr, fi = G.final_state(case, G.TRAVEL)
+        assert G.max_amp_err(re, im, fr, fi) < 1e-10
+        assert 1.0 - G.fidelity(re, im, fr, fi) < 1e-10
+    else:
+        idx, sr, si = G.samples(case, G.TRAVEL)
+        idx = idx.astype(np.int64)
+        assert float(max(np.max(np.abs(re[idx] - sr)), np.max(np.abs(im[idx] - si)))) < 1e-10
+        assert abs(float(np.dot(re, re) + np.dot(im, im)) - m["reference"]["norm2"]) < 1e-9
+    assert full["statistics"]["dmavm_kernel_ms_total"] > 0
+
+
+@pytest.mark.skipif(not CLI.exists(), reason="build/flatdd_gpu_standalone not built")
+def test_standalone_shots():
+    full, re, im = run(ROOT / "tests" / "circuits" / "ghz_n6.qasm", 1, extra=("--shots", "1000", "--seed", "5"))
+    assert set(full["samples_top16"].keys()) == {"000000", "111111"} and sum(full["samples_top16"].values()) == 1000
