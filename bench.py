@@ -385,7 +385,7 @@ def gpu_arm(args) -> int:
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{workload} array phase: DD->array conversion + {n_gates} fused DMAVM launches "
                                    f"({array_ops} circuit ops after the switch)" + (f" + {n_exch} half-shard exchanges" if world > 1 else ""),
-                       "n_qubits": n, "state_bytes": 16 << n, "fusion": "per gate (fuse 0)" if "_f0" in workload else "GPU-cost greedy (fuse 3)",
+                       "n_qubits": n, "state_bytes": 16 << n, "fusion": "per gate (fuse 0)" if "_f0" in workload else "dependency-graph fusion with the GPU cost model (fuse 4)",
                        "parallelism": "1 GPU" if world == 1 else f"state sharded over {world} GPUs by its top {world.bit_length() - 1} qubits; "
                                       f"qubit remap + half-shard exchange ({'peer-memory kernel' if method == 0 else 'NCCL send/recv'})",
                        "l2": f"shard ({(16 << n_local) >> 20} MiB) and its ping-pong partner exceed the 126 MB L2; no flush needed"

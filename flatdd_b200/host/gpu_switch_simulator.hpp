@@ -18,10 +18,13 @@
 // What is new:
 //   * fuse == 3: the same greedy control flow driven by the GPU cost model (fdd_cost_gpu: one
 //     launch costs max(HBM time, fp64 time) and a bound on the DD size), see DESIGN.md;
-//   * fuse == 4: dependency-graph fusion.  Operations on disjoint qubits commute, so a block is grown
-//     from ALL operations whose predecessors are done (not just the next one in program order) as long
-//     as it stays a cheap launch: at most 2 dense qubits (<= 4 non-zeros per row), at most 5
-//     non-diagonal qubits above the warp lanes (it still tiles) and a bounded DD;
+//   * fuse == 4: dependency-graph fusion (the product's default schedule).  Operations on disjoint qubits
+//     commute, so a block is grown from ALL operations whose predecessors are done (not just the next one
+//     in program order) as long as it stays a cheap launch: at most 4 dense qubits on at most 4
+//     non-diagonal qubits above the warp lanes (a 16-segment tile: the tensor-core path of the DMAVM
+//     kernel runs such a block at ~1.25 HBM passes whatever it holds, controls and phases on other
+//     qubits ride along through the context table), a bounded DD and a modelled time <= 2.2 passes.
+//     supremacy_n26: 58 launches for 5078 operations (fuse 3: 155), 25.5 ms instead of 75 ms;
 //   * identity gates (barriers) are detected and not launched; no memsets; no scratch arrays;
 //   * the state lives on the device; getVector materialises host arrays lazily.
 //

@@ -66,33 +66,34 @@ SHARDED = {
     "mix_n12_f3_w8": ("tests/circuits/mix_n12.qasm", 8, 3, 8),
     "brick_n11_f3_w2": ("tests/circuits/brick_n11.qasm", 8, 3, 2),
 }
-# traces only (host DD phase + fusion schedule, no reference array phase): name -> (circuit, fuse)
+# traces only (host DD phase + fusion schedule, no reference array phase): name -> (circuit, fuse[, shards]);
+# fuse 4 = dependency-graph fusion with the GPU cost model (the product's default schedule)
 TRACES = {
-    "supremacy_n26_gpu": (REF / "circuits/supremacy_n26.qasm", 3),
-    "supremacy_n26_gpu_w2": (REF / "circuits/supremacy_n26.qasm", 3, 2),
-    "supremacy_n26_gpu_w4": (REF / "circuits/supremacy_n26.qasm", 3, 4),
-    "supremacy_n26_gpu_w8": (REF / "circuits/supremacy_n26.qasm", 3, 8),
-    "supremacy_n20_gpu_w2": (REF / "circuits/supremacy_n20.qasm", 3, 2),
+    "supremacy_n26_gpu": (REF / "circuits/supremacy_n26.qasm", 4),
+    "supremacy_n26_gpu_w2": (REF / "circuits/supremacy_n26.qasm", 4, 2),
+    "supremacy_n26_gpu_w4": (REF / "circuits/supremacy_n26.qasm", 4, 4),
+    "supremacy_n26_gpu_w8": (REF / "circuits/supremacy_n26.qasm", 4, 8),
+    "supremacy_n20_gpu_w2": (REF / "circuits/supremacy_n20.qasm", 4, 2),
     "knn_n25_f0_w2": (REF / "circuits/knn_n25.qasm", 0, 2),
-    "synth_n26_w1": (ROOT / "oracle/_ref/circuits/synth_n26.qasm", 3, 1),
-    "synth_n26_w8": (ROOT / "oracle/_ref/circuits/synth_n26.qasm", 3, 8),
-    "synth_n30_w1": (ROOT / "oracle/_ref/circuits/synth_n30.qasm", 3, 1),
-    "synth_n30_w2": (ROOT / "oracle/_ref/circuits/synth_n30.qasm", 3, 2),
-    "synth_n30_w4": (ROOT / "oracle/_ref/circuits/synth_n30.qasm", 3, 4),
-    "synth_n30_w8": (ROOT / "oracle/_ref/circuits/synth_n30.qasm", 3, 8),
-    "synth_n34_w8": (ROOT / "oracle/_ref/circuits/synth_n34.qasm", 3, 8),
-    "synth_n20_w2": (ROOT / "oracle/_ref/circuits/synth_n20.qasm", 3, 2),
+    "synth_n26_w1": (ROOT / "oracle/_ref/circuits/synth_n26.qasm", 4, 1),
+    "synth_n26_w8": (ROOT / "oracle/_ref/circuits/synth_n26.qasm", 4, 8),
+    "synth_n30_w1": (ROOT / "oracle/_ref/circuits/synth_n30.qasm", 4, 1),
+    "synth_n30_w2": (ROOT / "oracle/_ref/circuits/synth_n30.qasm", 4, 2),
+    "synth_n30_w4": (ROOT / "oracle/_ref/circuits/synth_n30.qasm", 4, 4),
+    "synth_n30_w8": (ROOT / "oracle/_ref/circuits/synth_n30.qasm", 4, 8),
+    "synth_n34_w8": (ROOT / "oracle/_ref/circuits/synth_n34.qasm", 4, 8),
+    "synth_n20_w2": (ROOT / "oracle/_ref/circuits/synth_n20.qasm", 4, 2),
     "knn_n31_f0_w1": (REF / "circuits/knn_n31.qasm", 0, 1),
     "knn_n31_f0_w2": (REF / "circuits/knn_n31.qasm", 0, 2),
     "knn_n31_f0_w4": (REF / "circuits/knn_n31.qasm", 0, 4),
     "knn_n31_f0_w8": (REF / "circuits/knn_n31.qasm", 0, 8),
     "supremacy_n26_ref": (REF / "circuits/supremacy_n26.qasm", 1),
-    "supremacy_n24_gpu": (REF / "circuits/supremacy_n24.qasm", 3),
-    "supremacy_n20_gpu": (REF / "circuits/supremacy_n20.qasm", 3),
-    "dnn_n25_gpu": (REF / "circuits/dnn_n25.qasm", 3),
-    "knn_n25_gpu": (REF / "circuits/knn_n25.qasm", 3),
-    "swap_test_n25_gpu": (REF / "circuits/swap_test_n25.qasm", 3),
-    "vqe_n16_gpu": (REF / "circuits/vqe_n16.qasm", 3),
+    "supremacy_n24_gpu": (REF / "circuits/supremacy_n24.qasm", 4),
+    "supremacy_n20_gpu": (REF / "circuits/supremacy_n20.qasm", 4),
+    "dnn_n25_gpu": (REF / "circuits/dnn_n25.qasm", 4),
+    "knn_n25_gpu": (REF / "circuits/knn_n25.qasm", 4),
+    "swap_test_n25_gpu": (REF / "circuits/swap_test_n25.qasm", 4),
+    "vqe_n16_gpu": (REF / "circuits/vqe_n16.qasm", 4),
 }
 
 

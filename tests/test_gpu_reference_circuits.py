@@ -3,7 +3,7 @@ reference into oracle/_ref/golden/ (git-ignored, travels with the snapshot; rege
 `python oracle/make_golden.py medium|large`).  Cases that are not present are skipped.
 
 Two routes per circuit: (a) the boundary trace recorded next to the golden data replayed through
-the C-ABI, (b) the flatdd_gpu binary on the .qasm file with the GPU-cost fusion (--fuse 3), whose
+the C-ABI, (b) the flatdd_gpu binary on the .qasm file with the GPU-cost fusions (--fuse 3 and 4), whose
 schedule differs from the reference's but whose state must not."""
 import numpy as np
 import pytest
@@ -44,12 +44,13 @@ def test_trace_replay(case):
 
 
 @pytest.mark.skipif(not CLI.exists(), reason="build/flatdd_gpu not built")
+@pytest.mark.parametrize("fuse", [3, 4])
 @pytest.mark.parametrize("case", TRAVEL_CASES)
-def test_cli_gpu_fusion(case):
+def test_cli_gpu_fusion(case, fuse):
     m = G.manifest(case, G.TRAVEL)
     circuit = ROOT / "oracle" / "_ref" / "circuits" / m["circuit"]
     if not circuit.exists():
         pytest.skip(f"{circuit} not present")
-    out, stats, re, im, _ = run_cli(circuit, 16, 3, extra=("--quiet",))
+    out, stats, re, im, _ = run_cli(circuit, 16, fuse, extra=("--quiet",))
     assert stats["switched"] == m["reference"]["switched"]
     _check(case, re, im)

@@ -9,7 +9,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
 CLI = ROOT / "build" / "flatdd_gpu"
-fuse = sys.argv[1] if len(sys.argv) > 1 else "3"
+fuse = sys.argv[1] if len(sys.argv) > 1 else "4"
 names = ["ghz_state_n23", "vqe_n16", "dnn_n16", "dnn_n20", "supremacy_n20", "supremacy_n24", "knn_n25", "swap_test_n25", "dnn_n25",
          "supremacy_n26", "adder_n28", "knn_n31"]
 for name in names:
@@ -29,7 +29,7 @@ for name in names:
         print(json.dumps({"benchmark": name, "error": res.stderr[-300:]}))
         continue
     out = res.stdout
-    stats = json.loads(out[out.rindex("{\n  \"statistics\""):])["statistics"]
+    stats = json.loads(out[out.rindex("\n{\n") + 1:])["statistics"]
     stats["wall_s"] = wall
     stats["fuse"] = int(f)
     print(json.dumps(stats), flush=True)
