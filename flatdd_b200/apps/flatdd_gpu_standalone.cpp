@@ -3,11 +3,13 @@
 // flat gate-DD builder (flatdd_b200/host/standalone.hpp).  The state
 // starts flat on the device, every (fused) gate is a DMAVM launch through the C-ABI.
 //
-//   flatdd_gpu_standalone --file C.qasm [--fuse 0|1] [--max-block 5] [--max-nondiag 4] [--gpu D]
+//   flatdd_gpu_standalone --file C.qasm [--fuse 0|1|2] [--max-block 5] [--max-nondiag 4] [--gpu D]
 //                         [--bin FILE] [--pv] [--shots N --seed S] [--time-gates] [--quiet]
-//                         [--trace FILE [--trace-only]]
-// Flags of the reference that only steer its DD phase (-t, --thresh, --beta, --no_cache, --DDSIM_convert,
-// --ps) are accepted and ignored.  --trace-only records the boundary traffic without touching a GPU
+//                         [--trace FILE [--trace-only]] [--load STATE.bin]
+// --fuse 0: one launch per gate; 1: dense-block fusion with commuting open blocks; 2: dependency-graph dense-block fusion
+// (fewest launches).  Flags of the reference that only steer its DD phase (-t, --thresh, --beta, --no_cache, --DDSIM_convert,
+// --ps) are accepted and ignored.  --load resumes from a state written by --bin (checkpoint / resume).
+// --trace-only records the boundary traffic without touching a GPU
 // (used by the CPU tests: the trace is replayed on the oracle).
 #include "standalone.hpp"
 
@@ -33,7 +35,7 @@ struct Args {
 Args parseArgs(int argc, char** argv) {
     static const std::map<std::string, bool> takesValue = {
         {"file", true}, {"fuse", true}, {"t", true}, {"beta", true}, {"thresh", true}, {"gpu", true}, {"bin", true}, {"trace", true},
-        {"shots", true}, {"seed", true}, {"max-block", true}, {"max-nondiag", true}, {"pv", false}, {"ps", false}, {"no_cache", false},
+        {"shots", true}, {"seed", true}, {"load", true}, {"max-block", true}, {"max-nondiag", true}, {"pv", false}, {"ps", false}, {"no_cache", false},
         {"DDSIM_convert", false}, {"trace-only", false}, {"time-gates", false}, {"quiet", false}, {"help", false}, {"h", false}};
     Args a;
     for (int i = 1; i < argc; ++i) {
@@ -71,7 +73,7 @@ int main(int argc, char** argv) {
         return 1;
     }
     if (args.has("help") || args.has("h") || !args.has("file")) {
-        std::cout << "usage: flatdd_gpu_standalone --file C.qasm [--fuse 0|1] [--max-block 5] [--max-nondiag 4] [--gpu D] [--bin FILE] [--pv]\n"
+        std::cout << "usage: flatdd_gpu_standalone --file C.qasm [--fuse 0|1|2] [--max-block 5] [--max-nondiag 4] [--gpu D] [--bin FILE] [--pv]\n"
                      "                             [--shots N --seed S] [--time-gates] [--quiet] [--trace FILE [--trace-only]]\n";
         return args.has("file") ? 0 : 1;
     }
@@ -103,7 +105,20 @@ int main(int argc, char** argv) {
         sim.verbose = !args.has("quiet");
         sim.policy.maxBlockQubits = static_cast<int>(args.num("max-block", sim.policy.maxBlockQubits));
         sim.policy.maxNonDiagonal = static_cast<int>(args.num("max-nondiag", sim.policy.maxNonDiagonal));
-        if (sim.verbose) std::cout << "Starting flat on the device (no DD phase)" << std::endl;
+        if (args.has("load")) {
+            // resume: the initial state is a dump written by --bin (raw little-endian fp64: real array, then imag array)
+            if (!gpu) throw std::runtime_error("--load needs a GPU run");
+            const std::size_t dim = std::size_t{1} << nQubits;
+            std::vector<double> re(dim), im(dim);
+            std::ifstream in(args.str("load"), std::ios::binary);
+            if (!in.read(reinterpret_cast<char*>(re.data()), static_cast<std::streamsize>(dim * sizeof(double))) ||
+                !in.read(reinterpret_cast<char*>(im.data()), static_cast<std::streamsize>(dim * sizeof(double)))) {
+                throw std::runtime_error("--load: " + args.str("load") + " does not hold 2 x 2^n doubles");
+            }
+            fddb200::fddCheck(fdd_set_state(gpu->ctx(), re.data(), im.data()), "fdd_set_state");
+            sim.stateLoaded = true;
+        }
+        if (sim.verbose) std::cout << (sim.stateLoaded ? "Resuming from a dumped state" : "Starting flat on the device (no DD phase)") << std::endl;
         sim.simulate();
         const std::chrono::duration<float> durationSimulation = std::chrono::high_resolution_clock::now() - t1;
         std::cout << "Simulation finished" << std::endl;

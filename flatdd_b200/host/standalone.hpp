@@ -635,8 +635,9 @@ public:
     FlatStartSimulator(Circuit circuit, ArrayBackend* backend) : qc_(std::move(circuit)), backend_(backend) {}
 
     // knobs with the names of the reference simulator where they still mean something
-    unsigned fuse = 0;    // 0: one launch per gate; >= 1: dense-block fusion
+    unsigned fuse = 0;    // 0: one launch per gate; 1: dense-block fusion with commuting open blocks; >= 2: dependency-graph dense-block fusion
     bool verbose = true;
+    bool stateLoaded = false; // the backend already holds the initial state (resume from a dumped state)
     FusionPolicy policy;
 
     // results
@@ -649,7 +650,7 @@ public:
 
     void simulate() {
         const auto t0 = std::chrono::steady_clock::now();
-        backend_->convert(zeroStateDD(qc_.nQubits));
+        if (!stateLoaded) backend_->convert(zeroStateDD(qc_.nQubits));
         GateDDBuilder builder(qc_.nQubits);
         // Open blocks have pairwise disjoint qubit sets, so they commute: an operation only has to come after
         // the blocks it shares a qubit with, and the others stay open for later operations (a layer of
@@ -666,6 +667,16 @@ public:
             timeRecord2.push_back(seconds(a0));
             ++launches;
         };
+        if (fuse >= 2) {
+            simulateDag(emit);
+            backend_->synchronize();
+            arrayPhaseTime = seconds(t0) - gateMergingTime;
+            if (verbose) {
+                std::printf("Gate merging time: %g\n", gateMergingTime);
+                std::printf("Merged Gate Number: %zu\n", launches);
+            }
+            return;
+        }
         for (const Op& op : qc_.ops) {
             if (verbose && opIndex % 100 == 0) std::printf("[Instruction Count]  %zu\n", opIndex);
             ++opIndex;
@@ -735,6 +746,71 @@ private:
         Block block;
         int count = 0;
     };
+    // fuse >= 2: dependency-graph fusion.  Two operations are ordered only if they share a qubit; one block at a time is
+    // grown from ALL operations whose predecessors are done (earliest first) while the policy holds — the dense-block
+    // counterpart of GpuSwitchSimulator::buildScheduleDag.
+    template <class Emit> void simulateDag(Emit&& emit) {
+        std::vector<const Op*> ops;
+        for (const Op& op : qc_.ops) {
+            if (op.kind == Op::Measure || op.kind == Op::Barrier) continue;
+            if (op.kind == Op::Reset) throw std::runtime_error("reset is not supported");
+            ops.push_back(&op);
+        }
+        unitaryOps = ops.size();
+        const std::size_t count = ops.size();
+        std::vector<std::vector<std::size_t>> succ(count);
+        std::vector<int> indeg(count, 0);
+        {
+            std::vector<long> lastOn(static_cast<std::size_t>(qc_.nQubits), -1);
+            for (std::size_t i = 0; i < count; ++i) {
+                std::vector<long> preds;
+                for (int q : ops[i]->qubits) {
+                    const long p = lastOn[static_cast<std::size_t>(q)];
+                    if (p >= 0 && std::find(preds.begin(), preds.end(), p) == preds.end()) preds.push_back(p);
+                    lastOn[static_cast<std::size_t>(q)] = static_cast<long>(i);
+                }
+                for (long p : preds) {
+                    succ[static_cast<std::size_t>(p)].push_back(i);
+                    ++indeg[i];
+                }
+            }
+        }
+        std::vector<std::size_t> ready; // sorted: program order
+        for (std::size_t i = 0; i < count; ++i) {
+            if (indeg[i] == 0) ready.push_back(i);
+        }
+        std::size_t done = 0;
+        while (done < count) {
+            const auto m0 = std::chrono::steady_clock::now();
+            Open current;
+            bool progress = true;
+            while (progress) {
+                progress = false;
+                for (std::size_t r = 0; r < ready.size(); ++r) {
+                    const std::size_t i = ready[r];
+                    std::vector<int> sorted = ops[i]->qubits;
+                    std::sort(sorted.begin(), sorted.end());
+                    std::vector<int> all;
+                    std::set_union(sorted.begin(), sorted.end(), current.block.qubits.begin(), current.block.qubits.end(), std::back_inserter(all));
+                    if (current.count > 0 && static_cast<int>(all.size()) > policy.maxBlockQubits) continue;
+                    Block candidate = current.count > 0 ? multiply(blockOf(*ops[i]), current.block) : blockOf(*ops[i]);
+                    if (current.count > 0 && nonDiagonalCount(candidate) > policy.maxNonDiagonal) continue; // a block of one operation is always allowed
+                    current.block = std::move(candidate);
+                    ++current.count;
+                    ready.erase(ready.begin() + static_cast<std::ptrdiff_t>(r));
+                    for (std::size_t nxt : succ[i]) {
+                        if (--indeg[nxt] == 0) ready.insert(std::lower_bound(ready.begin(), ready.end(), nxt), nxt);
+                    }
+                    ++done;
+                    progress = true;
+                    break; // rescan from the earliest ready operation
+                }
+            }
+            gateMergingTime += seconds(m0);
+            if (current.count == 0) throw std::runtime_error("dependency-graph fusion made no progress");
+            emit(current);
+        }
+    }
     // first-fit packing of pairwise disjoint blocks into as few launches as the policy allows
     std::vector<Open> pack(std::vector<Open>& blocks) const {
         std::vector<Open> out;

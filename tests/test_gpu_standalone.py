@@ -34,7 +34,7 @@ def run(circuit: Path, fuse: int, extra=()):
 
 
 @pytest.mark.skipif(not CLI.exists(), reason="build/flatdd_gpu_standalone not built")
-@pytest.mark.parametrize("fuse", [0, 1])
+@pytest.mark.parametrize("fuse", [0, 1, 2])
 @pytest.mark.parametrize("name,golden", SMALL)
 def test_standalone_final_state(name, golden, fuse):
     full, re, im = run(ROOT / "tests" / "circuits" / f"{name}.qasm", fuse)
@@ -56,7 +56,7 @@ def test_standalone_on_reference_circuits(case):
     circuit = ROOT / "oracle" / "_ref" / "circuits" / m["circuit"]
     if not circuit.exists():
         pytest.skip(f"{circuit} not present")
-    full, re, im = run(circuit, 1, extra=("--time-gates",))
+    full, re, im = run(circuit, 2, extra=("--time-gates",))
     if (G.TRAVEL / case / "final_re.f64").exists():
         fr, fi = G.final_state(case, G.TRAVEL)
         assert G.max_amp_err(re, im, fr, fi) < 1e-10
@@ -73,3 +73,21 @@ def test_standalone_on_reference_circuits(case):
 def test_standalone_shots():
     full, re, im = run(ROOT / "tests" / "circuits" / "ghz_n6.qasm", 1, extra=("--shots", "1000", "--seed", "5"))
     assert set(full["samples_top16"].keys()) == {"000000", "111111"} and sum(full["samples_top16"].values()) == 1000
+
+
+@pytest.mark.skipif(not CLI.exists(), reason="build/flatdd_gpu_standalone not built")
+def test_standalone_dump_and_resume():
+    """--bin after the first half of a circuit, --load for the second half: the same final state as one run."""
+    lines = (ROOT / "tests" / "circuits" / "mix_n10.qasm").read_text().splitlines()
+    head = [ln for ln in lines if ln.startswith(("OPENQASM", "include", "qreg", "creg"))]
+    body = [ln for ln in lines if ln.strip() and not ln.startswith(("//", "OPENQASM", "include", "qreg", "creg", "measure"))]
+    with tempfile.TemporaryDirectory() as tmp:
+        first, second = Path(tmp) / "first.qasm", Path(tmp) / "second.qasm"
+        first.write_text("\n".join(head + body[: len(body) // 2]) + "\n")
+        second.write_text("\n".join(head + body[len(body) // 2:]) + "\n")
+        _, re1, im1 = run(first, 2)
+        dump = Path(tmp) / "half.bin"
+        np.concatenate([re1, im1]).astype("<f8").tofile(dump)
+        _, re2, im2 = run(second, 2, extra=("--load", str(dump)))
+    _, re, im = run(ROOT / "tests" / "circuits" / "mix_n10.qasm", 2)
+    assert G.max_amp_err(re, im, re2, im2) < 1e-13

@@ -1,5 +1,6 @@
-"""Runs build/flatdd_gpu on every reference circuit present under oracle/_ref/circuits and prints
-one JSON line per circuit (the CLI's own statistics block).  usage: python tools/run_all_circuits.py [fuse]"""
+"""Runs build/flatdd_gpu (or, with `standalone` as second argument, build/flatdd_gpu_standalone) on every reference
+circuit present under oracle/_ref/circuits and prints one JSON line per circuit (the CLI's own statistics block).
+usage: python tools/run_all_circuits.py [fuse] [standalone]"""
 import json
 import subprocess
 import sys
@@ -8,8 +9,9 @@ import time
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
-CLI = ROOT / "build" / "flatdd_gpu"
-fuse = sys.argv[1] if len(sys.argv) > 1 else "4"
+standalone = len(sys.argv) > 2 and sys.argv[2] == "standalone"
+CLI = ROOT / "build" / ("flatdd_gpu_standalone" if standalone else "flatdd_gpu")
+fuse = sys.argv[1] if len(sys.argv) > 1 else ("2" if standalone else "4")
 names = ["ghz_state_n23", "vqe_n16", "dnn_n16", "dnn_n20", "supremacy_n20", "supremacy_n24", "knn_n25", "swap_test_n25", "dnn_n25",
          "supremacy_n26", "adder_n28", "knn_n31"]
 for name in names:
@@ -22,8 +24,9 @@ for name in names:
         (Path(tmp) / "log" / "results" / "time").mkdir(parents=True)
         (Path(tmp) / "log" / "results" / "state").mkdir(parents=True)
         t0 = time.perf_counter()
-        f = "0" if name.startswith("knn_n31") else fuse  # cswap chains: per-gate, like the reference baseline plan
-        res = subprocess.run([str(CLI), "--file", str(circuit), "-t", "16", "--fuse", f, "--quiet"], cwd=cwd, capture_output=True, text=True)
+        # cswap chains: per-gate in the DD-driven binary, like the reference baseline plan (its DD-level fusion of cswap is slow)
+        f = "0" if name.startswith("knn_n31") and not standalone else fuse
+        res = subprocess.run([str(CLI), "--file", str(circuit), "-t", "16", "--fuse", f, "--quiet", "--time-gates"], cwd=cwd, capture_output=True, text=True)
         wall = time.perf_counter() - t0
     if res.returncode != 0:
         print(json.dumps({"benchmark": name, "error": res.stderr[-300:]}))
@@ -32,4 +35,5 @@ for name in names:
     stats = json.loads(out[out.rindex("\n{\n") + 1:])["statistics"]
     stats["wall_s"] = wall
     stats["fuse"] = int(f)
+    stats["cli"] = CLI.name
     print(json.dumps(stats), flush=True)
