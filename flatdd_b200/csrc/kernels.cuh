@@ -12,7 +12,9 @@
 // so neighbouring warps stream neighbouring DRAM pages.
 //
 // All arithmetic is IEEE fp64.  The conversion kernel uses un-fused multiplies and adds in the
-// reference's order (bit-identical results); DMAVM uses FMAs (tolerance 1e-10).
+// reference's order (bit-identical results); DMAVM uses FMAs, and FP64 tensor-core tiles (DMMA.8x8x4,
+// three real products per complex product) where a fused block is a real dense contraction on 3 or 4
+// upper qubits (tolerance 1e-10, measured <= 1e-13 against the reference; see DESIGN.md sections 3.2, 5).
 #pragma once
 
 #include "gate_compile.hpp"

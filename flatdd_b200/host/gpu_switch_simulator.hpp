@@ -57,6 +57,7 @@ struct FusionPolicy {
     // (non-zeros per row <= 2^maxDenseQubits) and this many non-diagonal qubits above the warp lanes
     int maxDenseQubits = 4;      // (4 dense qubits on <= 4 tile qubits: the tensor-core path, ~1.3 passes whatever the block holds)
     int maxTileQubits = 4;
+    int maxLaneWithTile = -1;    // >= 0: a block with tile qubits may be non-diagonal on at most this many warp-lane qubits
     double budgetFactor = 2.2;   // accept a block while its modelled time <= budgetFactor x the HBM time of one pass
 };
 
@@ -68,9 +69,9 @@ public:
 
     GpuSwitchSimulator(std::unique_ptr<Qc>&& circuit, ArrayBackend* backend_) : qc(std::move(circuit)), backend(backend_) {
         dd->resize(qc->getNqubits());
-        // experiments: FLATDD_B200_FUSE4="maxDenseQubits,maxTileQubits,budgetFactor" overrides the fuse == 4 policy
+        // experiments: FLATDD_B200_FUSE4="maxDenseQubits,maxTileQubits,budgetFactor[,maxLaneWithTile]" overrides the fuse == 4 policy
         if (const char* e = std::getenv("FLATDD_B200_FUSE4")) {
-            std::sscanf(e, "%d,%d,%lf", &policy.maxDenseQubits, &policy.maxTileQubits, &policy.budgetFactor);
+            std::sscanf(e, "%d,%d,%lf,%d", &policy.maxDenseQubits, &policy.maxTileQubits, &policy.budgetFactor, &policy.maxLaneWithTile);
         }
     }
 
@@ -569,7 +570,7 @@ private:
             }
             auto current = dd->makeIdent(qc->getNqubits());
             int currentCount = 0;
-            std::vector<int> dense, tile; // physical positions
+            std::vector<int> dense, tile, laneNd; // physical positions
             bool progress = true;
             while (progress) {
                 progress = false;
@@ -578,7 +579,7 @@ private:
                     const auto* op = ops[first + i].get();
                     if (needsGlobal(i)) continue;
                     // symbolic pre-check on the physical qubit sets
-                    std::vector<int> newDense = dense, newTile = tile;
+                    std::vector<int> newDense = dense, newTile = tile, newLane = laneNd;
                     if (!(worldSize > 1 && DdOps::isRelabelSwap(*op))) {
                         for (int q : DdOps::denseQubits(*op)) {
                             const int pq = physical(q);
@@ -588,13 +589,25 @@ private:
                         }
                         for (int q : DdOps::nonDiagonalQubits(*op)) {
                             const int pq = physical(q);
-                            if (pq < laneBits) continue;
+                            if (pq < laneBits) {
+                                bool haveLane = false;
+                                for (int x : newLane) haveLane = haveLane || x == pq;
+                                if (!haveLane) newLane.push_back(pq);
+                                continue;
+                            }
                             bool have = false;
                             for (int x : newTile) have = have || x == pq;
                             if (!have) newTile.push_back(pq);
                         }
                     }
                     if (static_cast<int>(newDense.size()) > policy.maxDenseQubits || static_cast<int>(newTile.size()) > policy.maxTileQubits) continue;
+                    if (policy.maxLaneWithTile >= 0 && !newTile.empty()) {
+                        // a block that mixes warp-lane qubits with tile qubits pays for the lane part in every tile segment
+                        // (shared-memory crossbar): bound the non-diagonal lane qubits of such a block
+                        int lane = 0;
+                        for (int x : newLane) lane += 1;
+                        if (lane > policy.maxLaneWithTile) continue;
+                    }
                     auto next = gateFor(op, &s.pending);
                     auto candidate = dd->multiply(next, current);
                     if (currentCount > 0) { // a block of one operation is always allowed
@@ -605,6 +618,7 @@ private:
                     ++currentCount;
                     dense.swap(newDense);
                     tile.swap(newTile);
+                    laneNd.swap(newLane);
                     ready.erase(ready.begin() + static_cast<long>(r));
                     for (std::size_t nxt : succ[i]) {
                         if (--indeg[nxt] == 0) ready.insert(std::lower_bound(ready.begin(), ready.end(), nxt), nxt);

@@ -80,3 +80,25 @@ def test_no_cpu_fallback():
 
 def test_comm_unique_id_has_nccl_size():
     assert len(load_library().comm_unique_id()) == 128
+
+
+def test_tile_facts_of_compiled_gates():
+    """Host analysis that selects the kernel path: tile bits, uniformity and the context bits of the tensor-core path."""
+    from tests import dd_builder as B
+    lib = load_library()
+    rng = np.random.default_rng(3)
+    dense = B.gate_dd(14, [13, 9, 6, 5], B.random_unitary(4, rng))
+    assert lib.matdd_info(dense, "tileable") == 1 and lib.matdd_info(dense, "uniform") == 1
+    assert lib.matdd_info(dense, "sub_tile_bits") == 4 and lib.matdd_info(dense, "max_paths") == 16
+    assert lib.matdd_info(dense, "context_bits") == 0 and lib.matdd_info(dense, "max_sub_k") == 1
+    # controls on qubits 12 and 7 (upper, outside the tile), dense on 14, 6, 9, 11: two context bits
+    ctrl = B.gate_dd(15, [12, 7, 14, 6, 9, 11], B.controlled(B.random_unitary(4, rng), 2))
+    assert lib.matdd_info(ctrl, "uniform") == 0 and lib.matdd_info(ctrl, "context_bits") == 2
+    assert lib.matdd_info(ctrl, "sub_tile_bits") == 4 and lib.matdd_info(ctrl, "non_diag_upper") == 4
+    # a control on a lane qubit is part of the sub table, not a context bit
+    lane = B.gate_dd(15, [2, 14, 6, 9, 11], B.controlled(B.random_unitary(4, rng), 1))
+    assert lib.matdd_info(lane, "context_bits") == 0 and lib.matdd_info(lane, "sub_tables") > 1
+    # the tensor-core classes are priced near one pass, a sub table per path clearly above
+    mem_ns = 32.0 * 2 ** 14 / 6500.0
+    assert (lib.cost_gpu(dense) - 3000.0) / mem_ns < 1.4
+    assert lib.cost_gpu(lane) > lib.cost_gpu(dense)
