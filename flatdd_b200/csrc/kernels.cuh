@@ -28,6 +28,9 @@
 #ifndef FDD_M5_3M
 #define FDD_M5_3M 1   // 1: three real DMMA products per complex product instead of four (measured 0.426 -> 0.417 ms at n = 26)
 #endif
+#ifndef FDD_M6_REGS
+#define FDD_M6_REGS 1 // flat-table path: weights of small tables in registers
+#endif
 #ifndef FDD_M5_STAGES
 #define FDD_M5_STAGES 2 // stage slots (sub-tiles) per warp
 #endif
@@ -910,6 +913,14 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(MODE == 5 
         __syncthreads();
     }
     if (warpGlobal >= p.nTiles) return;
+    // MODE 6 with a small table (rows x entries <= 16): the lane-private weights live in registers, which halves the
+    // shared-memory traffic of phase B (weights and gathered sources both cross the 128 B/clk crossbar otherwise)
+    constexpr bool FLAT_IN_REGS = MODE == 6 && FDD_M6_REGS && T * (KT > 0 ? KT : 1) <= 16;
+    double2 flatReg[FLAT_IN_REGS ? T * KT : 1];
+    if constexpr (FLAT_IN_REGS) {
+#pragma unroll
+        for (int i = 0; i < T * KT; ++i) flatReg[i] = flatW[i * 32 + lane];
+    }
 
     // everything above read only the gate tables; the state buffers belong to the previous launch until here
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -996,7 +1007,7 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(MODE == 5 
                 }
             }
         };
-        if (p.uniform) loadA(0);
+        if (p.uniform && !lookup) loadA(0); // (with a context table there is no entry area: the block comes from lookupA)
         for (uint32_t tile = warpGlobal; tile < p.nTiles; tile += warpStride) {
             const uint32_t base = depositAround(tile, wtMask);
             if (!p.uniform && !lookup) {
@@ -1189,7 +1200,11 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(MODE == 5 
                         for (int a = 0; a < NACC; ++a) {
                             const int t = (j0 + a) & (T - 1); // row inside the sub-tile (compile-time after unrolling)
                             const int at = (t * E + e) * 32 + lane;
-                            cmac(acc[a], flatW[at], stageOf(a)[flatC[at]]);
+                            if constexpr (FLAT_IN_REGS) {
+                                cmac(acc[a], flatReg[t * E + e], stageOf(a)[flatC[at]]);
+                            } else {
+                                cmac(acc[a], flatW[at], stageOf(a)[flatC[at]]);
+                            }
                         }
                     }
                 } else if (MODE == 4) {

@@ -1,6 +1,7 @@
 """Runs build/flatdd_gpu (or, with `standalone` as second argument, build/flatdd_gpu_standalone) on every reference
 circuit present under oracle/_ref/circuits and prints one JSON line per circuit (the CLI's own statistics block).
-usage: python tools/run_all_circuits.py [fuse] [standalone]"""
+usage: python tools/run_all_circuits.py [fuse] [standalone|dd] [time-gates]
+(time-gates synchronises after every launch to report per-launch device time; array_phase_time is then not representative)"""
 import json
 import subprocess
 import sys
@@ -26,7 +27,7 @@ for name in names:
         t0 = time.perf_counter()
         # cswap chains: per-gate in the DD-driven binary, like the reference baseline plan (its DD-level fusion of cswap is slow)
         f = "0" if name.startswith("knn_n31") and not standalone else fuse
-        res = subprocess.run([str(CLI), "--file", str(circuit), "-t", "16", "--fuse", f, "--quiet", "--time-gates"], cwd=cwd, capture_output=True, text=True)
+        res = subprocess.run([str(CLI), "--file", str(circuit), "-t", "16", "--fuse", f, "--quiet"] + (["--time-gates"] if "time-gates" in sys.argv[1:] else []), cwd=cwd, capture_output=True, text=True)
         wall = time.perf_counter() - t0
     if res.returncode != 0:
         print(json.dumps({"benchmark": name, "error": res.stderr[-300:]}))

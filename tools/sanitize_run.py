@@ -10,7 +10,11 @@ sys.path.insert(0, str(ROOT))
 from flatdd_b200 import Context, read_trace  # noqa: E402
 from oracle import pyoracle  # noqa: E402
 
+import os  # noqa: E402
+
 cases = ["tiny_n3_f1", "small_n5_f1", "qft_n8_f1", "mix_n10_f1", "mix_n12_f1", "mix_n12_f0"]
+if os.environ.get("SANITIZE_ONLY_NEW"):  # round 1b: only the tensor-core / context-table / flat-table paths below
+    cases = []
 for case in cases:
     n, records = read_trace(ROOT / "tests" / "golden" / case / "trace.bin")
     records = records[:40]
@@ -24,4 +28,25 @@ for case in cases:
             ctx.norm2()
         err = max(np.max(np.abs(re - orr)), np.max(np.abs(im - oi)))
         assert err < 1e-13, (case, variant, err)
+# tensor-core path (uniform, context table with 1-3 context bits, per-tile walk), flat-table path, MODE 3
+from tests import dd_builder as B  # noqa: E402
+
+rng = np.random.default_rng(0)
+shapes = [(10, [5, 6, 7, 8], 0), (11, [6, 8, 9], 0), (12, [10, 6, 5, 8, 11], 1), (13, [12, 7, 11, 6, 9, 10], 2), (12, [3, 8], 0), (12, [2, 7, 10], 0),
+          (12, [0, 3, 9, 11], 0)]
+for n, targets, n_ctrl in shapes:
+    u = B.random_unitary(len(targets) - n_ctrl, rng)
+    if n_ctrl:
+        u = B.controlled(u, n_ctrl)
+    gate = B.gate_dd(n, targets, u)
+    yr, yi = B.random_state(n, rng)
+    ref = B.apply_dense(n, targets, u, yr + 1j * yi)
+    for opts in ({}, {"context_table": 0}, {"dmma": 0}, {"flat_table": 0}):
+        with Context(n) as ctx:
+            for k, v in opts.items():
+                ctx.set_option(k, v)
+            ctx.set_state(yr, yi)
+            ctx.apply(gate)
+            re, im = ctx.get_state()
+        assert np.max(np.abs((re + 1j * im) - ref)) < 1e-13, (n, targets, opts)
 print("sanitize_run ok")
