@@ -35,7 +35,7 @@ struct Args {
 Args parseArgs(int argc, char** argv) {
     static const std::map<std::string, bool> takesValue = {
         {"file", true}, {"fuse", true}, {"t", true}, {"beta", true}, {"thresh", true}, {"gpu", true}, {"bin", true}, {"trace", true},
-        {"shots", true}, {"seed", true}, {"load", true}, {"max-block", true}, {"max-nondiag", true}, {"pv", false}, {"ps", false}, {"no_cache", false},
+        {"shots", true}, {"seed", true}, {"load", true}, {"max-block", true}, {"max-nondiag", true}, {"budget", true}, {"pv", false}, {"ps", false}, {"no_cache", false},
         {"DDSIM_convert", false}, {"trace-only", false}, {"time-gates", false}, {"quiet", false}, {"help", false}, {"h", false}};
     Args a;
     for (int i = 1; i < argc; ++i) {
@@ -105,6 +105,7 @@ int main(int argc, char** argv) {
         sim.verbose = !args.has("quiet");
         sim.policy.maxBlockQubits = static_cast<int>(args.num("max-block", sim.policy.maxBlockQubits));
         sim.policy.maxNonDiagonal = static_cast<int>(args.num("max-nondiag", sim.policy.maxNonDiagonal));
+        if (args.has("budget")) sim.policy.budgetFactor = std::stod(args.str("budget"));
         if (args.has("load")) {
             // resume: the initial state is a dump written by --bin (raw little-endian fp64: real array, then imag array)
             if (!gpu) throw std::runtime_error("--load needs a GPU run");

@@ -628,6 +628,8 @@ inline FlatVecDD zeroStateDD(int nQubits) {
 struct FusionPolicy {
     int maxBlockQubits = 5;  // qubits of one fused block (diagonal ones included)
     int maxNonDiagonal = 4;  // of which non-diagonal: sizes the kernel's tile (16 segments: the tensor-core path)
+    double budgetFactor = 2.2; // fuse 2: a block that touches a warp-lane qubit must stay within this many HBM passes (fdd_cost_gpu)
+    double hbmGBs = 6500.0;
 };
 
 class FlatStartSimulator {
@@ -795,6 +797,9 @@ private:
                     if (current.count > 0 && static_cast<int>(all.size()) > policy.maxBlockQubits) continue;
                     Block candidate = current.count > 0 ? multiply(blockOf(*ops[i]), current.block) : blockOf(*ops[i]);
                     if (current.count > 0 && nonDiagonalCount(candidate) > policy.maxNonDiagonal) continue; // a block of one operation is always allowed
+                    // blocks that stay above the warp lanes run at ~1.2-1.3 passes whatever they hold (tensor-core path); a block
+                    // that touches a lane qubit is priced by the GPU cost model, like GpuSwitchSimulator::buildScheduleDag does
+                    if (current.count > 0 && candidate.qubits.front() < 5 && !withinBudget(candidate)) continue;
                     current.block = std::move(candidate);
                     ++current.count;
                     ready.erase(ready.begin() + static_cast<std::ptrdiff_t>(r));
@@ -810,6 +815,17 @@ private:
             if (current.count == 0) throw std::runtime_error("dependency-graph fusion made no progress");
             emit(current);
         }
+    }
+    bool withinBudget(const Block& b) {
+        GateDDBuilder builder(qc_.nQubits);
+        const FlatMatDD dd = builder.build(b);
+        const fdd_matdd m = view(dd);
+        double ns = 0.0;
+        const int rc = fdd_cost_gpu(&m, policy.hbmGBs, 30000.0, &ns);
+        if (rc == FDD_ERR_TOO_DENSE) return false;
+        fddCheck(rc, "fdd_cost_gpu");
+        const double memNs = 32.0 * std::ldexp(1.0, qc_.nQubits) / policy.hbmGBs;
+        return ns - 3000.0 <= policy.budgetFactor * memNs; // 3000 ns = launch term of the model
     }
     // first-fit packing of pairwise disjoint blocks into as few launches as the policy allows
     std::vector<Open> pack(std::vector<Open>& blocks) const {
