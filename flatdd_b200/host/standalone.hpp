@@ -55,7 +55,7 @@ struct Circuit {
     std::string name;
     int nQubits = 0;
     int nClbits = 0;
-    std::vector<Op> ops; // one entry per statement, like qc::QuantumComputation::getNops()
+    std::vector<Op> ops; // one entry per statement like qc::QuantumComputation::getNops(); a broadcast gate is one entry per element
     [[nodiscard]] std::size_t nOps() const { return ops.size(); }
 };
 

@@ -87,3 +87,83 @@ def test_reader_rejects_what_it_does_not_support():
         q.write_text('OPENQASM 2.0;\nqreg q[2];\ngate foo a { h a; }\nfoo q[0];\n')
         with pytest.raises(subprocess.CalledProcessError):
             run_trace_only(q, 0)
+
+
+def _final_state(qasm_text: str, fuse: int):
+    with tempfile.TemporaryDirectory() as tmp:
+        q = Path(tmp) / "c.qasm"
+        q.write_text(qasm_text)
+        n, records, stats = run_trace_only(q, fuse)
+    re, im = pyoracle.replay_trace(records)
+    return n, re + 1j * im, stats
+
+
+def test_reader_registers_broadcast_and_expressions():
+    """Two quantum registers (first declared = low qubits), whole-register operands, parameter arithmetic."""
+    text = ('OPENQASM 2.0;\ninclude "qelib1.inc";\nqreg a[2];\nqreg b[3];\ncreg c[5];\n'
+            'h a;\n'                                   # broadcast: h a[0]; h a[1];  (one statement)
+            'rx(pi/2) b[0];\nry(-pi/4 + 0.5*2) b[1];\nrz(2^3/(1+3)) b[2];\nu3(sin(0.3),cos(0.2),sqrt(2)) a[1];\n'
+            'cx a, b[2];\n'                            # broadcast over the control register
+            'barrier a, b;\nmeasure b -> c;\n')
+    n, psi, stats = _final_state(text, 0)
+    assert n == 5 and stats["applied_gates"] == 10 and stats["unitary_gates"] == 8  # broadcast gates count per element; + barrier + measure
+    import math
+    from tests import dd_builder as B
+    h = np.array([[1, 1], [1, -1]]) / math.sqrt(2)
+
+    def rx(t): return np.array([[math.cos(t / 2), -1j * math.sin(t / 2)], [-1j * math.sin(t / 2), math.cos(t / 2)]])
+    def ry(t): return np.array([[math.cos(t / 2), -math.sin(t / 2)], [math.sin(t / 2), math.cos(t / 2)]])
+    def rz(t): return np.diag([np.exp(-0.5j * t), np.exp(0.5j * t)])
+    def u3(t, p, l): return np.array([[math.cos(t / 2), -np.exp(1j * l) * math.sin(t / 2)], [np.exp(1j * p) * math.sin(t / 2), np.exp(1j * (p + l)) * math.cos(t / 2)]])
+    cx = np.eye(4)[[0, 3, 2, 1]]  # dense index: bit 0 = control (targets[0]), bit 1 = target
+    ref = np.zeros(32, dtype=complex)
+    ref[0] = 1
+    for targets, m in [([0], h), ([1], h), ([2], rx(math.pi / 2)), ([3], ry(-math.pi / 4 + 1.0)), ([4], rz(2.0)),
+                       ([1], u3(math.sin(0.3), math.cos(0.2), math.sqrt(2))), ([0, 4], cx), ([1, 4], cx)]:
+        ref = B.apply_dense(5, targets, m, ref)
+    assert np.max(np.abs(psi - ref)) < 1e-14
+    for fuse in (1, 2):
+        _, fused, _ = _final_state(text, fuse)
+        assert np.max(np.abs(fused - ref)) < 1e-14
+
+
+def test_controlled_and_two_target_gates_match_dense_algebra():
+    """ccx / cswap / cu3 / crz / ccz / rzz / rxx / iswap / dcx against an independent numpy construction."""
+    import math
+    from tests import dd_builder as B
+    text = ('OPENQASM 2.0;\nqreg q[6];\n' + "".join(f"ry({0.3 + 0.2 * i}) q[{i}];\n" for i in range(6)) +
+            'ccx q[5],q[0],q[3];\ncswap q[1],q[4],q[2];\ncu3(0.4,0.5,0.6) q[3],q[5];\ncrz(0.7) q[0],q[4];\nccz q[2],q[1],q[0];\n'
+            'rzz(0.3) q[1],q[5];\nrxx(0.8) q[4],q[0];\niswap q[2],q[3];\ndcx q[5],q[1];\ncy q[0],q[2];\nch q[3],q[1];\nswap q[0],q[5];\n')
+    n, psi, _ = _final_state(text, 0)
+
+    def ry(t): return np.array([[math.cos(t / 2), -math.sin(t / 2)], [math.sin(t / 2), math.cos(t / 2)]])
+    def u3(t, p, l): return np.array([[math.cos(t / 2), -np.exp(1j * l) * math.sin(t / 2)], [np.exp(1j * p) * math.sin(t / 2), np.exp(1j * (p + l)) * math.cos(t / 2)]])
+    x = np.array([[0, 1], [1, 0]], dtype=complex)
+    y = np.array([[0, -1j], [1j, 0]])
+    z = np.diag([1.0, -1.0]).astype(complex)
+    h = np.array([[1, 1], [1, -1]], dtype=complex) / math.sqrt(2)
+    rz = lambda t: np.diag([np.exp(-0.5j * t), np.exp(0.5j * t)])
+    swap = np.eye(4)[[0, 2, 1, 3]].astype(complex)
+
+    def two(m4):  # reference convention: first listed qubit = high bit; dd_builder: targets[0] = bit 0 -> list the second qubit first
+        return m4
+    c, s = math.cos(0.15), math.sin(0.15)
+    rzz = np.diag([c - 1j * s, c + 1j * s, c + 1j * s, c - 1j * s])
+    c, s = math.cos(0.4), math.sin(0.4)
+    rxx = np.array([[c, 0, 0, -1j * s], [0, c, -1j * s, 0], [0, -1j * s, c, 0], [-1j * s, 0, 0, c]])
+    iswap = np.array([[1, 0, 0, 0], [0, 0, 1j, 0], [0, 1j, 0, 0], [0, 0, 0, 1]])
+    dcx = np.array([[1, 0, 0, 0], [0, 0, 0, 1], [0, 1, 0, 0], [0, 0, 1, 0]], dtype=complex)
+    ref = np.zeros(64, dtype=complex)
+    ref[0] = 1
+    for i in range(6):
+        ref = B.apply_dense(6, [i], ry(0.3 + 0.2 * i), ref)
+    steps = [([5, 0, 3], B.controlled(x, 2)), ([1, 2, 4], B.controlled(swap, 1)), ([3, 5], B.controlled(u3(0.4, 0.5, 0.6), 1)),
+             ([0, 4], B.controlled(rz(0.7), 1)), ([2, 1, 0], B.controlled(z, 2)),
+             ([5, 1], rzz), ([0, 4], rxx), ([3, 2], iswap), ([1, 5], dcx),   # two-target: dense bit 0 = second listed qubit
+             ([0, 2], B.controlled(y, 1)), ([3, 1], B.controlled(h, 1)), ([5, 0], swap)]
+    for targets, m in steps:
+        ref = B.apply_dense(6, targets, m, ref)
+    assert np.max(np.abs(psi - ref)) < 1e-14
+    for fuse in (1, 2):
+        _, fused, _ = _final_state(text, fuse)
+        assert np.max(np.abs(fused - ref)) < 1e-13
