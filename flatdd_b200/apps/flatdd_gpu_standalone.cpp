@@ -5,7 +5,7 @@
 //
 //   flatdd_gpu_standalone --file C.qasm [--fuse 0|1|2] [--max-block 5] [--max-nondiag 4] [--gpu D]
 //                         [--bin FILE] [--pv] [--shots N --seed S] [--time-gates] [--quiet]
-//                         [--trace FILE [--trace-only]] [--load STATE.bin]
+//                         [--trace FILE [--trace-only]] [--load STATE.bin] [--world N (with --trace-only: schedule for N shards)]
 // --fuse 0: one launch per gate; 1: dense-block fusion with commuting open blocks; 2: dependency-graph dense-block fusion
 // (fewest launches).  Flags of the reference that only steer its DD phase (-t, --thresh, --beta, --no_cache, --DDSIM_convert,
 // --ps) are accepted and ignored.  --load resumes from a state written by --bin (checkpoint / resume).
@@ -35,7 +35,7 @@ struct Args {
 Args parseArgs(int argc, char** argv) {
     static const std::map<std::string, bool> takesValue = {
         {"file", true}, {"fuse", true}, {"t", true}, {"beta", true}, {"thresh", true}, {"gpu", true}, {"bin", true}, {"trace", true},
-        {"shots", true}, {"seed", true}, {"load", true}, {"max-block", true}, {"max-nondiag", true}, {"budget", true}, {"pv", false}, {"ps", false}, {"no_cache", false},
+        {"shots", true}, {"seed", true}, {"load", true}, {"max-block", true}, {"max-nondiag", true}, {"budget", true}, {"world", true}, {"pv", false}, {"ps", false}, {"no_cache", false},
         {"DDSIM_convert", false}, {"trace-only", false}, {"time-gates", false}, {"quiet", false}, {"help", false}, {"h", false}};
     Args a;
     for (int i = 1; i < argc; ++i) {
@@ -87,6 +87,13 @@ int main(int argc, char** argv) {
         const std::size_t nOps = circuit.nOps();
         const std::string name = circuit.name;
         fddb200::ArrayBackend* backend = nullptr;
+        const int world = static_cast<int>(args.num("world", 1));
+        if (world > 1) {
+            // scheduling for a sharded state: qubit remaps and half-shard exchanges go into the trace; the multi-GPU run of a
+            // trace is bench.py / flatdd_b200.sharded.replay (one process per GPU), the multi-process CLI is flatdd_gpu
+            if (!args.has("trace-only") || !args.has("trace")) throw std::runtime_error("--world N schedules for N shards and needs --trace FILE --trace-only");
+            if ((world & (world - 1)) != 0 || world > 8) throw std::runtime_error("--world must be 2, 4 or 8");
+        }
         if (args.has("trace")) recorder = std::make_unique<fddb200::TraceRecorder>(args.str("trace"), nQubits);
         if (args.has("trace-only")) {
             if (!recorder) throw std::runtime_error("--trace-only needs --trace FILE");
@@ -100,7 +107,9 @@ int main(int argc, char** argv) {
                 backend = tee.get();
             }
         }
+        if (world > 1) recorder->setWorldSize(world);
         sa::FlatStartSimulator sim(std::move(circuit), backend);
+        sim.worldSize = world;
         sim.fuse = static_cast<unsigned>(args.num("fuse", 0));
         sim.verbose = !args.has("quiet");
         sim.policy.maxBlockQubits = static_cast<int>(args.num("max-block", sim.policy.maxBlockQubits));
@@ -180,6 +189,7 @@ int main(int argc, char** argv) {
         std::printf("    \"benchmark\": \"%s\",\n", name.c_str());
         std::printf("    \"dmavm_hbm_gbs\": %.6g,\n", sim.kernelMsTotal > 0 ? 32.0 * amps * static_cast<double>(sim.launches) / (sim.kernelMsTotal * 1e-3) / 1e9 : 0.0);
         std::printf("    \"dmavm_kernel_ms_total\": %.9g,\n", sim.kernelMsTotal);
+        std::printf("    \"exchanges\": %zu,\n", sim.exchanges);
         std::printf("    \"front_end\": \"standalone (flat start, dense-block fusion)\",\n");
         std::printf("    \"gate_merging_time\": %.9g,\n", sim.gateMergingTime);
         std::printf("    \"gates_per_sec_array_phase\": %.9g,\n", sim.arrayPhaseTime > 0 ? static_cast<double>(sim.unitaryOps) / sim.arrayPhaseTime : 0.0);

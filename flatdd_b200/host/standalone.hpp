@@ -472,6 +472,45 @@ inline int nonDiagonalCount(const Block& b) {
     return __builtin_popcountll(mask);
 }
 
+// non-diagonal qubits of a block (as qubit numbers)
+inline std::vector<int> nonDiagonalQubits(const Block& b) {
+    const std::size_t dim = b.dim();
+    std::size_t mask = 0;
+    for (std::size_t r = 0; r < dim; ++r) {
+        for (std::size_t c = 0; c < dim; ++c) {
+            if (b.m[r * dim + c] != cplx(0, 0)) mask |= r ^ c;
+        }
+    }
+    std::vector<int> out;
+    for (std::size_t i = 0; i < b.qubits.size(); ++i) {
+        if ((mask >> i) & 1) out.push_back(b.qubits[i]);
+    }
+    return out;
+}
+
+// the same block with qubit q renamed to map[q] (sharded states: logical -> physical positions)
+inline Block relabel(const Block& b, const std::vector<int>& map) {
+    const std::size_t k = b.qubits.size();
+    std::vector<int> renamed(k);
+    for (std::size_t i = 0; i < k; ++i) renamed[i] = map[static_cast<std::size_t>(b.qubits[i])];
+    Block out;
+    out.qubits = renamed;
+    std::sort(out.qubits.begin(), out.qubits.end());
+    std::vector<int> pos(k); // old bit i -> new bit pos[i]
+    for (std::size_t i = 0; i < k; ++i) pos[i] = static_cast<int>(std::lower_bound(out.qubits.begin(), out.qubits.end(), renamed[i]) - out.qubits.begin());
+    auto move = [&](std::size_t x) {
+        std::size_t v = 0;
+        for (std::size_t i = 0; i < k; ++i) v |= ((x >> i) & 1) << pos[i];
+        return v;
+    };
+    const std::size_t dim = b.dim();
+    out.m.assign(dim * dim, cplx(0, 0));
+    for (std::size_t r = 0; r < dim; ++r) {
+        for (std::size_t c = 0; c < dim; ++c) out.m[move(r) * dim + move(c)] = b.m[r * dim + c];
+    }
+    return out;
+}
+
 // ------------------------------------------------------------------------------------------------
 // dense block -> flat matrix DD (full depth, identity levels explicit, normalised so that equal
 // sub-blocks share nodes: a Kronecker product gets one node per level)
@@ -640,6 +679,12 @@ public:
     unsigned fuse = 0;    // 0: one launch per gate; 1: dense-block fusion with commuting open blocks; >= 2: dependency-graph dense-block fusion
     bool verbose = true;
     bool stateLoaded = false; // the backend already holds the initial state (resume from a dumped state)
+    // sharded state: the top log2(worldSize) PHYSICAL qubits are global.  Blocks are built in
+    // physical positions; an operation that is non-diagonal on a global qubit first swaps it with the local qubit
+    // whose next non-diagonal use lies furthest ahead (Belady), like GpuSwitchSimulator::planExchanges.  fuse >= 2 only.
+    int worldSize = 1;
+    std::size_t lookahead = 4096;
+    std::size_t exchanges = 0;
     FusionPolicy policy;
 
     // results
@@ -669,6 +714,7 @@ public:
             timeRecord2.push_back(seconds(a0));
             ++launches;
         };
+        if (worldSize > 1 && fuse < 2) throw std::runtime_error("a sharded state needs the dependency-graph schedule (--fuse 2)");
         if (fuse >= 2) {
             simulateDag(emit);
             backend_->synchronize();
@@ -781,21 +827,76 @@ private:
         for (std::size_t i = 0; i < count; ++i) {
             if (indeg[i] == 0) ready.push_back(i);
         }
+        // sharded: logical -> physical map and the non-diagonal (logical) qubits of every operation
+        int globalBits = 0;
+        while ((1 << globalBits) < worldSize) ++globalBits;
+        const int local = qc_.nQubits - globalBits;
+        std::vector<int> perm(static_cast<std::size_t>(qc_.nQubits));
+        for (int q = 0; q < qc_.nQubits; ++q) perm[static_cast<std::size_t>(q)] = q;
+        std::vector<std::vector<int>> nonDiag;
+        if (worldSize > 1) {
+            if (local < 5) throw std::runtime_error("a shard must hold at least 5 qubits");
+            for (const Op* op : ops) nonDiag.push_back(nonDiagonalQubits(blockOf(*op)));
+        }
+        auto needsGlobal = [&](std::size_t i) {
+            if (worldSize <= 1) return false;
+            for (int q : nonDiag[i]) {
+                if (perm[static_cast<std::size_t>(q)] >= local) return true;
+            }
+            return false;
+        };
+        auto planExchanges = [&](std::size_t k) {
+            for (int q : nonDiag[k]) {
+                const int pq = perm[static_cast<std::size_t>(q)];
+                if (pq < local) continue;
+                int victim = -1, victimPos = -1;
+                std::size_t victimUse = 0;
+                const int floorPos = local > 6 ? 3 : 0; // runs shorter than 128 bytes waste NVLink sectors
+                for (int cand = 0; cand < qc_.nQubits; ++cand) {
+                    const int pc = perm[static_cast<std::size_t>(cand)];
+                    if (pc >= local || pc < floorPos) continue;
+                    if (std::find(nonDiag[k].begin(), nonDiag[k].end(), cand) != nonDiag[k].end()) continue;
+                    std::size_t use = k + 1 + lookahead; // "never" within the window
+                    for (std::size_t j = k + 1; j < count && j <= k + lookahead; ++j) {
+                        if (std::find(nonDiag[j].begin(), nonDiag[j].end(), cand) != nonDiag[j].end()) {
+                            use = j;
+                            break;
+                        }
+                    }
+                    if (victim < 0 || use > victimUse || (use == victimUse && pc > victimPos)) {
+                        victim = cand;
+                        victimUse = use;
+                        victimPos = pc;
+                    }
+                }
+                if (victim < 0) throw std::runtime_error("no local qubit available for the exchange (gate touches too many qubits)");
+                backend_->exchange(pq, victimPos);
+                ++exchanges;
+                std::swap(perm[static_cast<std::size_t>(q)], perm[static_cast<std::size_t>(victim)]);
+            }
+        };
+        auto physicalBlock = [&](const Op& op) { return worldSize > 1 ? relabel(blockOf(op), perm) : blockOf(op); };
         std::size_t done = 0;
         while (done < count) {
             const auto m0 = std::chrono::steady_clock::now();
+            if (worldSize > 1) {
+                // if nothing ready can run under the current layout, remap for the earliest ready operation
+                bool any = false;
+                for (std::size_t i : ready) any = any || !needsGlobal(i);
+                if (!any) planExchanges(ready.front());
+            }
             Open current;
             bool progress = true;
             while (progress) {
                 progress = false;
                 for (std::size_t r = 0; r < ready.size(); ++r) {
                     const std::size_t i = ready[r];
-                    std::vector<int> sorted = ops[i]->qubits;
-                    std::sort(sorted.begin(), sorted.end());
+                    if (needsGlobal(i)) continue;
+                    const Block next = physicalBlock(*ops[i]);
                     std::vector<int> all;
-                    std::set_union(sorted.begin(), sorted.end(), current.block.qubits.begin(), current.block.qubits.end(), std::back_inserter(all));
+                    std::set_union(next.qubits.begin(), next.qubits.end(), current.block.qubits.begin(), current.block.qubits.end(), std::back_inserter(all));
                     if (current.count > 0 && static_cast<int>(all.size()) > policy.maxBlockQubits) continue;
-                    Block candidate = current.count > 0 ? multiply(blockOf(*ops[i]), current.block) : blockOf(*ops[i]);
+                    Block candidate = current.count > 0 ? multiply(next, current.block) : next;
                     if (current.count > 0 && nonDiagonalCount(candidate) > policy.maxNonDiagonal) continue; // a block of one operation is always allowed
                     // blocks that stay above the warp lanes run at ~1.2-1.3 passes whatever they hold (tensor-core path); a block
                     // that touches a lane qubit is priced by the GPU cost model, like GpuSwitchSimulator::buildScheduleDag does

@@ -167,3 +167,37 @@ def test_controlled_and_two_target_gates_match_dense_algebra():
     for fuse in (1, 2):
         _, fused, _ = _final_state(text, fuse)
         assert np.max(np.abs(fused - ref)) < 1e-13
+
+
+SHARDED_CASES = [("mix_n10", "mix_n10_f0", 2), ("mix_n10", "mix_n10_f0", 8), ("brick_n11", "brick_n11_f1", 2), ("mix_n12", "mix_n12_f0", 4),
+                 ("qft_n8", "qft_n8_f0", 4)]
+
+
+@pytest.mark.parametrize("name,golden,world", SHARDED_CASES)
+def test_standalone_sharded_schedule_on_global_model(name, golden, world):
+    """--world N: the standalone front end schedules for N shards (blocks in physical qubit order, Belady remap, half-shard
+    exchanges); the trace replayed on the global-array model of tests/test_sharded_cpu.py gives the reference's state."""
+    from flatdd_b200.sharded import replay, to_logical_order
+    from tests.test_sharded_cpu import GlobalModel
+    n, records, stats = run_trace_only(ROOT / "tests" / "circuits" / f"{name}.qasm", 2, ("--world", str(world)))
+    n_local = n - int(np.log2(world))
+    model = GlobalModel(n, n_local)  # asserts that every gate is diagonal on the global qubits
+    l2p = replay(records, model, n)
+    got = to_logical_order(model.re + 1j * model.im, l2p)
+    fr, fi = G.final_state(golden)
+    assert np.max(np.abs(got - (fr + 1j * fi))) < 1e-10
+    n_exchanges = sum(r.kind == 3 for r in records)
+    assert n_exchanges == stats["exchanges"] and n_exchanges >= 1  # these circuits do act on their top qubits
+    for r in records:
+        if r.kind == 3:
+            assert r.exchange[0] >= n_local > r.exchange[1] >= 0
+
+
+def test_standalone_sharded_needs_dag_schedule_and_trace_only():
+    with tempfile.TemporaryDirectory() as tmp:
+        q = ROOT / "tests" / "circuits" / "mix_n10.qasm"
+        with pytest.raises(subprocess.CalledProcessError):
+            run_trace_only(q, 1, ("--world", "2"))
+        cwd = Path(tmp)
+        res = subprocess.run([str(build_cli()), "--file", str(q), "--fuse", "2", "--world", "2", "--quiet"], cwd=cwd, capture_output=True, text=True)
+        assert res.returncode != 0 and "trace-only" in res.stderr
