@@ -64,12 +64,15 @@ public:
     using std::runtime_error::runtime_error;
 };
 
+// true when the name is one of the built-in gates (with any number of leading 'c' controls)
+inline bool isBuiltinGate(const std::string& name);
+
 namespace detail {
 
 // arithmetic of gate parameters: + - * / ^, unary minus, parentheses, pi, sin cos tan exp ln sqrt
 class Expr {
 public:
-    explicit Expr(const std::string& s) : s_(s) {}
+    explicit Expr(const std::string& s, const std::map<std::string, double>* vars = nullptr) : s_(s), vars_(vars) {}
     double parse() {
         const double v = sum();
         skip();
@@ -129,6 +132,10 @@ private:
         while (pos_ < s_.size() && (std::isalnum(static_cast<unsigned char>(s_[pos_])) || s_[pos_] == '_')) id += s_[pos_++];
         if (id == "pi") return M_PI;
         if (id.empty()) throw QasmError("cannot parse parameter '" + s_ + "'");
+        if (vars_ != nullptr) { // formal parameter of a gate definition
+            const auto it = vars_->find(id);
+            if (it != vars_->end()) return it->second;
+        }
         if (!eat('(')) throw QasmError("unknown identifier '" + id + "' in parameter");
         const double a = sum();
         if (!eat(')')) throw QasmError("missing ')' in parameter '" + s_ + "'");
@@ -141,6 +148,7 @@ private:
         throw QasmError("unknown function '" + id + "'");
     }
     const std::string& s_;
+    const std::map<std::string, double>* vars_;
     std::size_t pos_ = 0;
 };
 
@@ -180,7 +188,41 @@ inline Circuit parseQasm(std::istream& in, const std::string& name) {
         text += (cut == std::string::npos ? line : line.substr(0, cut));
         text += '\n';
     }
-    if (text.find('{') != std::string::npos) throw QasmError("gate definitions / blocks are not supported by the standalone reader");
+    // gate definitions: `gate name(params) qargs { body }` are cut out of the text and expanded at every use (macro
+    // semantics of OpenQASM 2); anything else with a block (if / opaque bodies) is rejected
+    struct GateDef {
+        std::vector<std::string> params, qargs, body;
+    };
+    std::map<std::string, GateDef> defs;
+    for (;;) {
+        const auto open = text.find('{');
+        if (open == std::string::npos) break;
+        const auto close = text.find('}', open);
+        if (close == std::string::npos) throw QasmError("missing '}'");
+        auto start = text.rfind(';', open);
+        start = start == std::string::npos ? 0 : start + 1;
+        std::string head = detail::trim(text.substr(start, open - start));
+        if (head.rfind("gate", 0) != 0 || head.size() < 5 || !std::isspace(static_cast<unsigned char>(head[4]))) {
+            throw QasmError("only gate definitions may have a block: '" + head + "'");
+        }
+        head = detail::trim(head.substr(4));
+        GateDef def;
+        std::size_t p = 0;
+        while (p < head.size() && (std::isalnum(static_cast<unsigned char>(head[p])) || head[p] == '_')) ++p;
+        const std::string gname = head.substr(0, p);
+        std::string rest = detail::trim(head.substr(p));
+        if (!rest.empty() && rest[0] == '(') {
+            const auto rp = rest.find(')');
+            if (rp == std::string::npos) throw QasmError("missing ')' in gate definition " + gname);
+            def.params = detail::splitTop(rest.substr(1, rp - 1), ',');
+            rest = detail::trim(rest.substr(rp + 1));
+        }
+        def.qargs = detail::splitTop(rest, ',');
+        def.body = detail::splitTop(text.substr(open + 1, close - open - 1), ';');
+        if (gname.empty() || def.qargs.empty()) throw QasmError("malformed gate definition '" + head + "'");
+        defs[gname] = def;
+        text.erase(start, close + 1 - start);
+    }
     struct Reg {
         int first, size;
     };
@@ -200,6 +242,48 @@ inline Circuit parseQasm(std::istream& in, const std::string& name) {
             out.push_back(it->second.first + idx);
         }
         return out;
+    };
+    // a use of a defined gate is replaced by its body with parameters and qubits substituted, recursively
+    std::function<void(const Op&, int)> expand = [&](const Op& use, int depth) {
+        const auto it = defs.find(use.name);
+        if (it == defs.end() || isBuiltinGate(use.name)) {
+            c.ops.push_back(use);
+            return;
+        }
+        const GateDef& def = it->second;
+        if (depth > 64) throw QasmError("gate definitions nest too deeply (recursive definition of '" + use.name + "'?)");
+        if (use.params.size() != def.params.size() || use.qubits.size() != def.qargs.size()) {
+            throw QasmError("gate " + use.name + " used with the wrong number of parameters or qubits");
+        }
+        std::map<std::string, double> vars;
+        for (std::size_t i = 0; i < def.params.size(); ++i) vars[def.params[i]] = use.params[i];
+        for (const std::string& rawBody : def.body) {
+            const std::string st = detail::trim(rawBody);
+            if (st.empty()) continue;
+            std::size_t p = 0;
+            while (p < st.size() && (std::isalnum(static_cast<unsigned char>(st[p])) || st[p] == '_')) ++p;
+            Op inner;
+            inner.name = st.substr(0, p);
+            if (inner.name == "barrier") continue;
+            std::string rest = detail::trim(st.substr(p));
+            if (!rest.empty() && rest[0] == '(') {
+                int level = 0;
+                std::size_t close = 0;
+                for (; close < rest.size(); ++close) {
+                    if (rest[close] == '(') ++level;
+                    if (rest[close] == ')' && --level == 0) break;
+                }
+                if (close == rest.size()) throw QasmError("missing ')' in the body of gate " + use.name);
+                for (const auto& e : detail::splitTop(rest.substr(1, close - 1), ',')) inner.params.push_back(detail::Expr(e, &vars).parse());
+                rest = detail::trim(rest.substr(close + 1));
+            }
+            for (const auto& formal : detail::splitTop(rest, ',')) {
+                const auto at = std::find(def.qargs.begin(), def.qargs.end(), formal);
+                if (at == def.qargs.end()) throw QasmError("unknown qubit '" + formal + "' in the body of gate " + use.name);
+                inner.qubits.push_back(use.qubits[static_cast<std::size_t>(at - def.qargs.begin())]);
+            }
+            expand(inner, depth + 1);
+        }
     };
     for (const std::string& raw : detail::splitTop(text, ';')) {
         const std::string st = detail::trim(raw);
@@ -263,7 +347,7 @@ inline Circuit parseQasm(std::istream& in, const std::string& name) {
         for (std::size_t b = 0; b < broadcast; ++b) {
             Op one = op;
             for (const auto& a : args) one.qubits.push_back(a.size() > 1 ? a[b] : a[0]);
-            c.ops.push_back(one);
+            expand(one, 0);
         }
     }
     if (c.nQubits == 0) throw QasmError("no qreg declared");
@@ -351,6 +435,28 @@ inline bool twoQubitMatrix(const std::string& g, const std::vector<double>& p, M
 }
 
 } // namespace detail
+
+inline bool isBuiltinGate(const std::string& name) {
+    static const char* const one[] = {"id", "i", "x", "y", "z", "h", "s", "sdg", "t", "tdg", "sx", "sxdg", "rx", "ry", "rz", "p", "u1", "phase", "u2", "u3", "u", "U"};
+    static const char* const two[] = {"swap", "iswap", "dcx", "rzz", "rxx", "ryy", "rzx"};
+    std::string base = name;
+    if (base == "CX" || base == "cnot") base = "cx";
+    if (base == "toffoli") base = "ccx";
+    if (base == "fredkin") base = "cswap";
+    for (;;) {
+        for (const char* g : one) {
+            if (base == g) return true;
+        }
+        for (const char* g : two) {
+            if (base == g) return true;
+        }
+        if (base.size() > 1 && base[0] == 'c') {
+            base = base.substr(1);
+            continue;
+        }
+        return false;
+    }
+}
 
 // The operation as a dense block on its own qubits.  Leading 'c's of the name are controls
 // (cx, ccx, cswap, cu3, ...), the rest is a one- or two-target base gate.

@@ -84,7 +84,10 @@ def test_reader_rejects_what_it_does_not_support():
         q.write_text('OPENQASM 2.0;\nqreg q[2];\nfoo q[0];\n')
         with pytest.raises(subprocess.CalledProcessError):
             run_trace_only(q, 0)
-        q.write_text('OPENQASM 2.0;\nqreg q[2];\ngate foo a { h a; }\nfoo q[0];\n')
+        q.write_text('OPENQASM 2.0;\nqreg q[2];\ncreg c[2];\nif(c==1) x q[0];\n')
+        with pytest.raises(subprocess.CalledProcessError):
+            run_trace_only(q, 0)
+        q.write_text('OPENQASM 2.0;\nqreg q[2];\ngate foo a { foo a; }\nfoo q[0];\n')  # recursive definition
         with pytest.raises(subprocess.CalledProcessError):
             run_trace_only(q, 0)
 
@@ -201,3 +204,41 @@ def test_standalone_sharded_needs_dag_schedule_and_trace_only():
         cwd = Path(tmp)
         res = subprocess.run([str(build_cli()), "--file", str(q), "--fuse", "2", "--world", "2", "--quiet"], cwd=cwd, capture_output=True, text=True)
         assert res.returncode != 0 and "trace-only" in res.stderr
+
+
+def test_gate_definitions_expand_like_macros():
+    """`gate` blocks: parameters and qubits are substituted at every use, definitions may use each other."""
+    import math
+    from tests import dd_builder as B
+    text = ('OPENQASM 2.0;\ninclude "qelib1.inc";\n'
+            'gate rot(theta, phi) a { ry(theta/2) a; rz(phi + pi/4) a; }\n'
+            'gate entangle(t) a, b { rot(t, 2*t) a; cx a, b; rot(-t, 0.1) b; barrier a, b; }\n'
+            'gate bell a, b { h a; cx a, b; }\n'
+            'qreg q[4];\nbell q[0], q[3];\nentangle(0.6) q[1], q[2];\nentangle(pi/3) q[3], q[0];\nrot(0.2, 0.3) q;\n')
+    n, psi, stats = _final_state(text, 0)
+    assert stats["unitary_gates"] == 2 + 5 + 5 + 8
+
+    def ry(t): return np.array([[math.cos(t / 2), -math.sin(t / 2)], [math.sin(t / 2), math.cos(t / 2)]])
+    def rz(t): return np.diag([np.exp(-0.5j * t), np.exp(0.5j * t)])
+    h = np.array([[1, 1], [1, -1]]) / math.sqrt(2)
+    cx = np.eye(4)[[0, 3, 2, 1]]
+    ref = np.zeros(16, dtype=complex)
+    ref[0] = 1
+
+    def rot(state, t, p, q):
+        state = B.apply_dense(4, [q], ry(t / 2), state)
+        return B.apply_dense(4, [q], rz(p + math.pi / 4), state)
+
+    def entangle(state, t, a, b):
+        state = rot(state, t, 2 * t, a)
+        state = B.apply_dense(4, [a, b], cx, state)
+        return rot(state, -t, 0.1, b)
+    ref = B.apply_dense(4, [0], h, ref)
+    ref = B.apply_dense(4, [0, 3], cx, ref)
+    ref = entangle(ref, 0.6, 1, 2)
+    ref = entangle(ref, math.pi / 3, 3, 0)
+    for q in range(4):
+        ref = rot(ref, 0.2, 0.3, q)
+    assert np.max(np.abs(psi - ref)) < 1e-14
+    _, fused, _ = _final_state(text, 2)
+    assert np.max(np.abs(fused - ref)) < 1e-14
