@@ -18,7 +18,7 @@
 // What is new:
 //   * fuse == 3: the same greedy control flow driven by the GPU cost model (fdd_cost_gpu: one
 //     launch costs max(HBM time, fp64 time) and a bound on the DD size), see DESIGN.md;
-//   * fuse == 4: dependency-graph fusion (the product's default schedule).  Operations on disjoint qubits
+//   * fuse == 4: dependency-graph fusion (the schedule of bench.py and of the committed traces).  Operations on disjoint qubits
 //     commute, so a block is grown from ALL operations whose predecessors are done (not just the next one
 //     in program order) as long as it stays a cheap launch: at most 4 dense qubits on at most 4
 //     non-diagonal qubits above the warp lanes (a 16-segment tile: the tensor-core path of the DMAVM

@@ -65,13 +65,13 @@ SHARDED = {
     "mix_n12_f1_w4": ("tests/circuits/mix_n12.qasm", 8, 1, 4),
     "mix_n12_f3_w8": ("tests/circuits/mix_n12.qasm", 8, 3, 8),
     "brick_n11_f3_w2": ("tests/circuits/brick_n11.qasm", 8, 3, 2),
-    # the dependency-graph fusion (the product's default schedule) under sharding
+    # the dependency-graph fusion (the schedule bench.py measures) under sharding
     "brick_n11_f4_w2": ("tests/circuits/brick_n11.qasm", 8, 4, 2),
     "mix_n12_f4_w4": ("tests/circuits/mix_n12.qasm", 8, 4, 4),
     "mix_n10_f4_w8": ("tests/circuits/mix_n10.qasm", 4, 4, 8),
 }
 # traces only (host DD phase + fusion schedule, no reference array phase): name -> (circuit, fuse[, shards]);
-# fuse 4 = dependency-graph fusion with the GPU cost model (the product's default schedule)
+# fuse 4 = dependency-graph fusion with the GPU cost model (the schedule bench.py measures)
 TRACES = {
     "supremacy_n26_gpu": (REF / "circuits/supremacy_n26.qasm", 4),
     "supremacy_n26_gpu_w2": (REF / "circuits/supremacy_n26.qasm", 4, 2),
