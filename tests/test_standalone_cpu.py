@@ -242,3 +242,33 @@ def test_gate_definitions_expand_like_macros():
     assert np.max(np.abs(psi - ref)) < 1e-14
     _, fused, _ = _final_state(text, 2)
     assert np.max(np.abs(fused - ref)) < 1e-14
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fusion_is_state_preserving_on_random_circuits(seed):
+    """Random circuits over the whole gate set (1-, 2-, 3-qubit gates, all qubit positions incl. the warp-lane qubits):
+    every fusion mode, several policies and a sharded schedule give the state of the unfused run."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_circuits", ROOT / "tests" / "circuits" / "gen_circuits.py")
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    n = 6 + seed % 5  # 6..10 qubits
+    text = "\n".join(gen.header(n, f"rand{seed}") + gen.random_circuit(n, 90, seed=1000 + seed) + gen.footer(n)) + "\n"
+    _, ref, stats0 = _final_state(text, 0)
+    assert abs(np.vdot(ref, ref).real - 1.0) < 1e-12
+    with tempfile.TemporaryDirectory() as tmp:
+        q = Path(tmp) / "c.qasm"
+        q.write_text(text)
+        for fuse, extra in [(1, ()), (2, ()), (1, ("--max-block", "3", "--max-nondiag", "2")), (2, ("--max-block", "6", "--max-nondiag", "3")),
+                            (2, ("--budget", "1.3"))]:
+            _, records, stats = run_trace_only(q, fuse, extra)
+            re, im = pyoracle.replay_trace(records)
+            assert np.max(np.abs((re + 1j * im) - ref)) < 1e-12, (fuse, extra)
+            assert stats["array_phase_launches"] <= stats0["array_phase_launches"]
+        if n - 1 >= 5:  # two shards need five local qubits
+            from flatdd_b200.sharded import replay, to_logical_order
+            from tests.test_sharded_cpu import GlobalModel
+            _, records, _ = run_trace_only(q, 2, ("--world", "2"))
+            model = GlobalModel(n, n - 1)
+            l2p = replay(records, model, n)
+            assert np.max(np.abs(to_logical_order(model.re + 1j * model.im, l2p) - ref)) < 1e-12
