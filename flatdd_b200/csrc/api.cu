@@ -1024,9 +1024,12 @@ int fdd_set_zero_state(fdd_ctx* ctx) {
         if (ctx == nullptr) throw std::invalid_argument("ctx is null");
         useDevice(ctx);
         const uint64_t dim = ctx->localDim();
-        zero_state_kernel<<<gridFor(ctx, dim, 256), 256, 0, ctx->stream>>>(ctx->buf[ctx->cur], dim, ctx->rank == 0 ? 1 : 0);
+        // written into the idle buffer and flipped like every other initialiser, so the ping-pong parity of the ranks of a
+        // sharded state never depends on how each one was initialised (the exchange kernel reads the partner's buf[cur])
+        zero_state_kernel<<<gridFor(ctx, dim, 256), 256, 0, ctx->stream>>>(ctx->buf[ctx->cur ^ 1], dim, ctx->rank == 0 ? 1 : 0);
         CUDA_TRY(cudaGetLastError());
         ctx->launches++;
+        ctx->cur ^= 1;
         ctx->hasState = true;
         for (int q = 0; q < ctx->n; ++q) ctx->logicalToPhysical[static_cast<size_t>(q)] = q;
     });

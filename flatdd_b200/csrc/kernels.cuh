@@ -866,8 +866,9 @@ template <int TB, int MODE, int KT> __global__ void __launch_bounds__(MODE == 5 
             }
         }
     };
-    if (p.uniform) {
+    if (p.uniform && !lookup) {
         // every tile sees the same lists: warp 0 walks once for the whole CTA
+        // (with a context table there is no entry area to walk into: the blocks come from lookupA)
         if (warp == 0) walkTile(0u);
         __syncthreads();
     }

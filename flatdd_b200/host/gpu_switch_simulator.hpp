@@ -216,6 +216,18 @@ private:
         for (int q = 0; q < nq(); ++q) perm[static_cast<typename Perm::key_type>(q)] = static_cast<typename Perm::mapped_type>(q);
         for (const auto& op : qc->ops) nonDiag.push_back(DdOps::nonDiagonalQubits(*op));
     }
+    // Sharded mode: user-defined gates arrive as compound operations.  dd::getDD(compound, dd, perm) would absorb an
+    // uncontrolled SWAP inside one into `perm` without telling the backend, and the exchange planner would judge the
+    // later sub-operations by the layout before that SWAP.  So from the first array-phase operation on, compound
+    // operations are replaced by their sub-operations, each of which goes through planExchanges / gateFor on its own.
+    // (The DD phase keeps the circuit as parsed: the switch rule counts operations like the reference.)
+    void expandCompoundFrom(std::size_t from) {
+        if (worldSize <= 1) return;
+        if (DdOps::expandCompound(*qc, from)) {
+            nonDiag.clear();
+            for (const auto& op : qc->ops) nonDiag.push_back(DdOps::nonDiagonalQubits(*op));
+        }
+    }
     // one layout change: exchange == true moves data (half-shard exchange), false only renames
     struct LayoutStep {
         bool exchange;
@@ -358,6 +370,7 @@ private:
                 const double ddSize = static_cast<double>(dd->size(rootEdge));
                 if (emaSwitchTest(ddSize)) {
                     doSwitch(opNum);
+                    expandCompoundFrom(k + 1);
                     arrayStart = Clock::now();
                 }
                 EMA_v = pendingEma;
@@ -608,9 +621,10 @@ private:
                         for (int x : newLane) lane += 1;
                         if (lane > policy.maxLaneWithTile) continue;
                     }
+                    const bool relabelOnly = worldSize > 1 && DdOps::isRelabelSwap(*op); // free: no launch, no data movement
                     auto next = gateFor(op, &s.pending);
                     auto candidate = dd->multiply(next, current);
-                    if (currentCount > 0) { // a block of one operation is always allowed
+                    if (currentCount > 0 && !relabelOnly) { // a block of one operation is always allowed
                         const Cost c = gpuCost(candidate);
                         if (static_cast<double>(c.value) - 3000.0 > policy.budgetFactor * memNs) continue; // 3000 ns = launch term of the model
                     }
@@ -683,6 +697,7 @@ private:
                 if (emaSwitchTest(ddSize)) {
                     doSwitch(opNum);
                     const auto tm = Clock::now();
+                    expandCompoundFrom(opNum + 1);
                     schedule = buildSchedule(opNum + 1);
                     gateMergingTime = since(tm);
                     if (verbose) {
@@ -706,6 +721,7 @@ private:
 
     // enable_switch == false (src/SwitchSimulator.cpp:415-587): array from the first gate on
     void runAllArray(bool ignoreNonUnitaries) {
+        expandCompoundFrom(0);
         getVectorFromDD();
         switched = true;
         switchedAtOp = 0;

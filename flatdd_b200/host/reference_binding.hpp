@@ -91,6 +91,24 @@ struct RefDdOps {
         for (const auto& c : op.getControls()) out.push_back(static_cast<int>(c.qubit));
         return out;
     }
+    // replaces every compound operation from index `from` on by clones of its sub-operations (recursively)
+    static bool expandCompound(qc::QuantumComputation& circuit, std::size_t from) {
+        bool changed = false;
+        auto& ops = circuit.ops;
+        for (std::size_t k = from; k < ops.size();) {
+            const auto* compound = dynamic_cast<const qc::CompoundOperation*>(ops[k].get());
+            if (compound == nullptr) {
+                ++k;
+                continue;
+            }
+            std::vector<std::unique_ptr<qc::Operation>> subs;
+            for (const auto& sub : *compound) subs.push_back(sub->clone());
+            ops.erase(ops.begin() + static_cast<std::ptrdiff_t>(k));
+            ops.insert(ops.begin() + static_cast<std::ptrdiff_t>(k), std::make_move_iterator(subs.begin()), std::make_move_iterator(subs.end()));
+            changed = true; // k stays: a nested compound operation is expanded on the next pass
+        }
+        return changed;
+    }
     static bool isMeasure(const qc::Operation& op) { return op.getType() == qc::Measure; }
     static bool isBarrier(const qc::Operation& op) { return op.getType() == qc::Barrier; }
     static bool isReset(const qc::Operation& op) { return op.getType() == qc::Reset; }

@@ -66,6 +66,7 @@ public:
 
 // true when the name is one of the built-in gates (with any number of leading 'c' controls)
 inline bool isBuiltinGate(const std::string& name);
+inline bool isStandardGate(const std::string& name);
 
 namespace detail {
 
@@ -246,7 +247,9 @@ inline Circuit parseQasm(std::istream& in, const std::string& name) {
     // a use of a defined gate is replaced by its body with parameters and qubits substituted, recursively
     std::function<void(const Op&, int)> expand = [&](const Op& use, int depth) {
         const auto it = defs.find(use.name);
-        if (it == defs.end() || isBuiltinGate(use.name)) {
+        // a definition in the file wins unless the name is a base gate or one of qelib1's own controlled gates
+        // (whose bodies the built-in matrices reproduce); a user gate that merely looks like "c" + gate keeps its body
+        if (it == defs.end() || isStandardGate(use.name)) {
             c.ops.push_back(use);
             return;
         }
@@ -341,7 +344,10 @@ inline Circuit parseQasm(std::istream& in, const std::string& name) {
         std::size_t broadcast = 1;
         for (const auto& tok : detail::splitTop(rest, ',')) {
             args.push_back(operand(tok, qregs));
-            if (args.back().size() > 1) broadcast = args.back().size();
+            if (args.back().size() > 1) {
+                if (broadcast > 1 && args.back().size() != broadcast) throw QasmError("registers of different sizes in '" + st + "'");
+                broadcast = args.back().size();
+            }
         }
         if (args.empty()) throw QasmError("gate without operands: '" + st + "'");
         for (std::size_t b = 0; b < broadcast; ++b) {
@@ -456,6 +462,16 @@ inline bool isBuiltinGate(const std::string& name) {
         }
         return false;
     }
+}
+
+// Names whose meaning is fixed by the language or by qelib1.inc: the base gates and qelib1's controlled gates.
+inline bool isStandardGate(const std::string& name) {
+    static const char* const controlled[] = {"CX", "cnot", "toffoli", "fredkin", "cx", "cy", "cz", "ch", "ccx", "cswap", "crx", "cry", "crz",
+                                             "cu1", "cp", "cu3", "csx", "c3x", "c4x"};
+    for (const char* g : controlled) {
+        if (name == g) return true;
+    }
+    return isBuiltinGate(name) && !(name.size() > 1 && name[0] == 'c' && isBuiltinGate(name.substr(1)));
 }
 
 // The operation as a dense block on its own qubits.  Leading 'c's of the name are controls

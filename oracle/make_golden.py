@@ -38,6 +38,9 @@ SMALL = {
     "brick_n11_f1": ("tests/circuits/brick_n11.qasm", 8, 1, ["--kat-gates", "1"]),
     "mix_n12_f0": ("tests/circuits/mix_n12.qasm", 8, 0, ["--kat-gates", "1"]),
     "mix_n12_f1": ("tests/circuits/mix_n12.qasm", 8, 1, ["--kat-gates", "1"]),
+    # user-defined gates (compound operations) with SWAPs inside
+    "compound_n9_f0": ("tests/circuits/compound_n9.qasm", 4, 0, ["--kat-gates", "1"]),
+    "compound_n9_f1": ("tests/circuits/compound_n9.qasm", 4, 1, ["--kat-gates", "1"]),
 }
 MEDIUM = {
     "synth_n20_f1": (ROOT / "oracle/_ref/circuits/synth_n20.qasm", 8, 1, ["--no-kat", "--samples", "65536"]),
@@ -69,6 +72,11 @@ SHARDED = {
     "brick_n11_f4_w2": ("tests/circuits/brick_n11.qasm", 8, 4, 2),
     "mix_n12_f4_w4": ("tests/circuits/mix_n12.qasm", 8, 4, 4),
     "mix_n10_f4_w8": ("tests/circuits/mix_n10.qasm", 4, 4, 8),
+    # compound operations are expanded in sharded mode (a SWAP inside one renames qubits mid-operation)
+    "compound_n9_f0_w2": ("tests/circuits/compound_n9.qasm", 4, 0, 2),
+    "compound_n9_f1_w4": ("tests/circuits/compound_n9.qasm", 4, 1, 4),
+    "compound_n9_f4_w2": ("tests/circuits/compound_n9.qasm", 4, 4, 2),
+    "compound_n9_f4_w8": ("tests/circuits/compound_n9.qasm", 4, 4, 8),
 }
 # traces only (host DD phase + fusion schedule, no reference array phase): name -> (circuit, fuse[, shards]);
 # fuse 4 = dependency-graph fusion with the GPU cost model (the schedule bench.py measures)
