@@ -6,8 +6,8 @@ one B200.  One STEP = one pass of the hot path over that circuit: the DD->array 
 state DD at the reference's switch point (after op 911) plus one DMAVM launch per fused gate of
 the schedule (5078 circuit operations in the array phase).  The inputs are the flat DD tables the
 host driver (flatdd_b200/host/gpu_switch_simulator.hpp) emits for that circuit, recorded at build
-time into a boundary trace (oracle/_ref/traces/, a committed copy under tests/golden/traces/);
-nothing here reads /root/reference.
+time into a boundary trace by the product's own binary (`build/flatdd_gpu --trace-only`, committed under
+bench_inputs/traces/); nothing here reads /root/reference.
 
 Metric: array-phase circuit operations per second ("gates/s"); seconds per circuit is echoed.
   value  kernels only, gate tables resident in HBM (compiled once), CUDA events on the library stream
@@ -48,17 +48,12 @@ UNIT = "gates/s"
 # workload
 # ------------------------------------------------------------------------------------------------
 def find_trace(name: str) -> Path:
-    travel = ROOT / "oracle" / "_ref" / "traces" / name / "trace.bin"
-    if travel.exists():
-        return travel
-    packed = ROOT / "tests" / "golden" / "traces" / f"{name}.trace.gz"
+    """Boundary traces are made by the product's own host driver (`build/flatdd_gpu --trace-only`,
+    tools/make_bench_inputs.py) and committed gzip'd under bench_inputs/traces/."""
+    packed = ROOT / "bench_inputs" / "traces" / f"{name}.trace.gz"
     if packed.exists():
-        out = Path(tempfile.gettempdir()) / f"flatdd_b200_{name}.trace.bin"
-        if not out.exists() or out.stat().st_mtime < packed.stat().st_mtime:
-            with gzip.open(packed, "rb") as src, open(out, "wb") as dst:
-                shutil.copyfileobj(src, dst)
-        return out
-    raise FileNotFoundError(f"no boundary trace for {name}: run `python oracle/make_golden.py traces` where the reference tree exists")
+        return packed
+    raise FileNotFoundError(f"no boundary trace for {name}: run `python tools/make_bench_inputs.py {name}` where build/flatdd_gpu exists")
 
 
 def table_bytes(dd) -> int:
@@ -199,7 +194,31 @@ def reference_arm(args) -> int:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def gpu_arm(args) -> int:
+def trace_name_for(workload: str, world: int) -> str:
+    if workload.startswith("supremacy"):  # fused with the GPU cost model
+        return f"{workload}_gpu" if world == 1 else f"{workload}_gpu_w{world}"
+    if workload.startswith("synth"):
+        return f"{workload}_w{world}"
+    return f"{workload}_w{world}"  # e.g. knn_n31_f0: per-gate traces exist for every shard count, also _w1
+
+
+def reference_samples(workload: str):
+    """Sampled amplitudes of the reference's own final state (oracle/ref_dump run of the unmodified reference,
+    published to bench_inputs/samples/ by `python oracle/make_golden.py publish`): (indices, complex values) or None."""
+    import numpy as np
+    f = ROOT / "bench_inputs" / "samples" / f"{workload}.samples.bin"
+    if not f.exists():
+        return None
+    raw = f.read_bytes()
+    cnt = int(np.frombuffer(raw, dtype="<u8", count=1)[0])
+    idx = np.frombuffer(raw, dtype="<u8", count=cnt, offset=8)
+    re = np.frombuffer(raw, dtype="<f8", count=cnt, offset=8 + 8 * cnt)
+    im = np.frombuffer(raw, dtype="<f8", count=cnt, offset=8 + 16 * cnt)
+    return idx, re + 1j * im
+
+
+def measure(workload: str, args, steps: int, warmup: int, with_e2e: bool) -> dict | None:
+    """Times one workload on the ranks of this job; rank 0 gets the result dict, the others None."""
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -209,22 +228,9 @@ def gpu_arm(args) -> int:
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world == 1 and args.gpus > 1:
-        raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: flatdd_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-
     lib = load_library()
-    workload = args.workload
-    if workload.startswith("supremacy"):  # fused with the GPU cost model
-        trace_name = f"{workload}_gpu" if world == 1 else f"{workload}_gpu_w{world}"
-    else:  # e.g. knn_n31_f0: per-gate traces exist for every shard count, also _w1
-        trace_name = f"{workload}_w{world}"
-    n, records = read_trace(find_trace(trace_name))
+    n, records = read_trace(find_trace(trace_name_for(workload, world)))
     assert records[0].kind == 1
     vec = records[0].dd
     array_ops = sum(r.n_original_gates for r in records if r.kind == 2)
@@ -242,19 +248,19 @@ def gpu_arm(args) -> int:
         key, value = kv.split("=")
         ctx.set_option(key, int(value))
     stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
-    steps = []  # ("g", [compiled gates of one schedule segment]) | ("x", global bit, local bit) | ("r", a, b)
+    sched = []  # ("g", [compiled gates of one schedule segment]) | ("x", global bit, local bit) | ("r", a, b)
     for r in records[1:]:
         if r.kind == 2:
-            if steps and steps[-1][0] == "g":
-                steps[-1][1].append(ctx.compile(r.dd))
+            if sched and sched[-1][0] == "g":
+                sched[-1][1].append(ctx.compile(r.dd))
             else:
-                steps.append(("g", [ctx.compile(r.dd)]))
+                sched.append(("g", [ctx.compile(r.dd)]))
         elif r.kind == 3:
-            steps.append(("x",) + tuple(r.exchange))
+            sched.append(("x",) + tuple(r.exchange))
         elif r.kind == 4:
-            steps.append(("r",) + tuple(r.exchange))
-    n_gates = sum(len(s[1]) for s in steps if s[0] == "g")
-    n_exch = sum(1 for s in steps if s[0] == "x")
+            sched.append(("r",) + tuple(r.exchange))
+    n_gates = sum(len(s[1]) for s in sched if s[0] == "g")
+    n_exch = sum(1 for s in sched if s[0] == "x")
     method = args.exchange_method
 
     def barrier():
@@ -265,8 +271,7 @@ def gpu_arm(args) -> int:
             torch.cuda.synchronize()
 
     def step_resident(exchange_events=None):
-        ctx.convert(vec)
-        for s in steps:
+        for s in sched:
             if s[0] == "g":
                 ctx.apply_compiled_many(s[1])
             elif s[0] == "x":
@@ -281,132 +286,231 @@ def gpu_arm(args) -> int:
             else:
                 ctx.relabel_qubits(s[1], s[2])
 
-    warmup = max(3, args.warmup)
     for _ in range(warmup):
+        ctx.convert(vec)
         step_resident()
     barrier()
 
     # ---- timed region: K steps, device time on the library's stream ---------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * steps)]
     exchange_events = []
     launches0 = ctx.launch_count()
+    tensor0 = ctx.get_option("tensor_core_launches")
     barrier()
-    for s in range(args.steps):
+    for s in range(steps):
         ev[3 * s].record(stream)
         ctx.convert(vec)
         ev[3 * s + 1].record(stream)
-        for st in steps:
-            if st[0] == "g":
-                ctx.apply_compiled_many(st[1])
-            elif st[0] == "x":
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                ctx.exchange_qubits(st[1], st[2], method)
-                e1.record(stream)
-                exchange_events.append((e0, e1))
-            else:
-                ctx.relabel_qubits(st[1], st[2])
+        step_resident(exchange_events)
         ev[3 * s + 2].record(stream)
     barrier()
     launches = ctx.launch_count() - launches0
-    total_ms = ev[0].elapsed_time(ev[3 * args.steps - 1])
-    convert_ms = [ev[3 * s].elapsed_time(ev[3 * s + 1]) for s in range(args.steps)]
-    body_ms = [ev[3 * s + 1].elapsed_time(ev[3 * s + 2]) for s in range(args.steps)]
+    tensor_launches = ctx.get_option("tensor_core_launches") - tensor0
+    total_ms = ev[0].elapsed_time(ev[3 * steps - 1])
+    convert_ms = [ev[3 * s].elapsed_time(ev[3 * s + 1]) for s in range(steps)]
+    body_ms = [ev[3 * s + 1].elapsed_time(ev[3 * s + 2]) for s in range(steps)]
     exch_ms = [a.elapsed_time(b) for a, b in exchange_events]
     norm2 = ctx.norm2()
 
     # ---- e2e: host buffers through the C-ABI, H2D of every table and D2H of the state ------------
-    gates = [r.dd for r in records if r.kind == 2]
-    h2d = table_bytes(vec) + sum(table_bytes(g) for g in gates)
-    download = local_dim if n_local <= 28 else 1 << 20  # very large shards: a 16 MiB sample of the state
-    host_re = torch.empty(local_dim if download == local_dim else download, dtype=torch.float64).pin_memory()
-    host_im = torch.empty_like(host_re).pin_memory()
-    d2h = 16 * download
+    e2e_s, e2e_steps, h2d, d2h, host_norm2 = None, 0, 0, 0, None
+    if with_e2e:
+        gates = [r.dd for r in records if r.kind == 2]
+        h2d = table_bytes(vec) + sum(table_bytes(g) for g in gates)
+        download = local_dim if n_local <= 28 else 1 << 20  # very large shards: a 16 MiB sample of the state
+        host_re = torch.empty(download, dtype=torch.float64).pin_memory()
+        host_im = torch.empty_like(host_re).pin_memory()
+        d2h = 16 * download
 
-    def step_e2e():
-        ctx.convert(vec)
-        for r in records[1:]:
-            if r.kind == 2:
-                ctx.apply(r.dd)
-            elif r.kind == 3:
-                ctx.exchange_qubits(r.exchange[0], r.exchange[1], method)
+        def step_e2e():
+            ctx.convert(vec)
+            for r in records[1:]:
+                if r.kind == 2:
+                    ctx.apply(r.dd)
+                elif r.kind == 3:
+                    ctx.exchange_qubits(r.exchange[0], r.exchange[1], method)
+                else:
+                    ctx.relabel_qubits(*r.exchange)
+            if world > 1:
+                ctx.canonicalize()  # what getVector does for a sharded state: rank r = amplitudes with top index bits r
+            if download == local_dim:
+                ctx.get_state_raw(host_re.data_ptr(), host_im.data_ptr())
             else:
-                ctx.relabel_qubits(*r.exchange)
-        if download == local_dim:
-            ctx.get_state_raw(host_re.data_ptr(), host_im.data_ptr())
-        else:
-            amps = ctx.get_amplitudes(0, download)
-            host_re.copy_(torch.from_numpy(np.ascontiguousarray(amps.real)))
-            host_im.copy_(torch.from_numpy(np.ascontiguousarray(amps.imag)))
+                amps = ctx.get_amplitudes(0, download)
+                host_re.copy_(torch.from_numpy(np.ascontiguousarray(amps.real)))
+                host_im.copy_(torch.from_numpy(np.ascontiguousarray(amps.imag)))
 
-    step_e2e()
-    barrier()
-    e2e_steps = max(1, min(args.steps, 3))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
         step_e2e()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+        barrier()
+        e2e_steps = max(1, min(steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        host_norm2 = float(torch.dot(host_re, host_re) + torch.dot(host_im, host_im))
     clocks = sampler.stop()
-    host_norm2 = float(torch.dot(host_re, host_re) + torch.dot(host_im, host_im))
+
+    # ---- parity inside the bench: the state this run produced against the reference's own sampled amplitudes ----
+    ref = reference_samples(workload)
+    amp_err, n_checked = None, 0
+    if ref is not None:
+        if world > 1:
+            ctx.canonicalize()
+        idx, want = ref
+        mine = (idx >> np.uint64(n_local)) == np.uint64(rank)
+        got = ctx.get_amplitudes_at(idx[mine] & np.uint64(local_dim - 1))
+        amp_err = float(np.max(np.abs(got - want[mine]))) if mine.any() else 0.0
+        n_checked = int(mine.sum())
 
     # ---- max over ranks / sums ---------------------------------------------------------------------
-    t_step_ms = total_ms / args.steps
+    t_step_ms = total_ms / steps
     exch_mean_ms = statistics.mean(exch_ms) if exch_ms else 0.0
+    body_mean = statistics.mean(body_ms)
     if world > 1:
-        t = torch.tensor([t_step_ms, e2e_s, exch_mean_ms, statistics.mean(body_ms)], dtype=torch.float64, device=device)
+        t = torch.tensor([t_step_ms, e2e_s or 0.0, exch_mean_ms, body_mean, amp_err or 0.0], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_step_ms, e2e_s, exch_mean_ms, body_mean = (float(x) for x in t)
-        nt = torch.tensor([norm2, host_norm2], dtype=torch.float64, device=device)
+        t_step_ms, e2e_max, exch_mean_ms, body_mean, amp_err_max = (float(x) for x in t)
+        e2e_s = e2e_max if e2e_s is not None else None
+        amp_err = amp_err_max if amp_err is not None else None
+        nt = torch.tensor([norm2, host_norm2 or 0.0, float(n_checked)], dtype=torch.float64, device=device)
         dist.all_reduce(nt, op=dist.ReduceOp.SUM)
-        norm2, host_norm2 = float(nt[0]), float(nt[1])
+        norm2, host_sum, n_checked = float(nt[0]), float(nt[1]), int(nt[2])
+        host_norm2 = host_sum if host_norm2 is not None else None
+    ctx.close()
+    if rank != 0:
+        return None
+
+    peaks = {}
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        peaks = json.loads(peaks_file.read_text())
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # DMAVM launch time: the step body minus the exchanges
+    launch_ms = (body_mean - exch_mean_ms * n_exch) / max(1, n_gates)
+    achieved = 32.0 * local_dim / (launch_ms * 1e-3) / 1e9
+    traffic = None
+    tf = ROOT / "profiles" / "dmavm_traffic.json"
+    if tf.exists() and n_local == 26:
+        traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+    res = {
+        "workload": workload, "n_qubits": n, "n_gates": n_gates, "n_exch": n_exch, "array_ops": array_ops, "n_local": n_local,
+        "value": array_ops / (t_step_ms * 1e-3), "ms_per_step": t_step_ms, "convert_ms": statistics.mean(convert_ms),
+        "dmavm_ms_per_launch": launch_ms, "launches": int(launches), "tensor_core_launches": int(tensor_launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "kernel": "dmavm_tile_kernel", "peak_source": peak_src, "bytes_per_launch": 32 * local_dim,
+                     "convert_gbs": 16.0 * local_dim / (statistics.mean(convert_ms) * 1e-3) / 1e9},
+        "check": {"norm2_device": norm2, "max_amp_err_vs_reference": amp_err, "reference_samples_checked": n_checked,
+                  "reference": "unmodified reference FlatDD (oracle/ref_dump), sampled amplitudes in bench_inputs/samples/"
+                               if amp_err is not None else "no reference samples for this workload (norm only)"},
+    }
+    if host_norm2 is not None:
+        res["check"]["norm2_host_copy"] = host_norm2
+    if with_e2e:
+        res["e2e"] = {"value": array_ops / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                      "seconds_per_circuit": e2e_s, "steps": e2e_steps}
+    if world > 1 and n_exch:
+        half_bytes = 8.0 * local_dim
+        gbs = half_bytes / (exch_mean_ms * 1e-3) / 1e9
+        res["exchange"] = {"per_step": n_exch, "bytes_each_way_per_gpu": half_bytes, "ms_mean": exch_mean_ms, "gbs_per_direction": gbs,
+                           "frac_of_nvlink_nominal_900": gbs / 900.0, "frac_of_nvlink_measured_770": gbs / 770.0,
+                           "method": "peer-memory kernel (flags in peer memory, no NCCL call)" if method == 0 else "NCCL send/recv + D2D copy"}
+    return res
+
+
+def circuit_wall(threads: int) -> dict:
+    """Whole-circuit wall clock of the drop-in binary: `build/flatdd_gpu --fuse 4` on the .qasm file, the reference's own
+    `simulation_time` definition (from before the parse to after simulate(), apps/FlatDD.cpp:46,75,113-120)."""
+    exe = ROOT / "build" / "flatdd_gpu"
+    circuit = ROOT / "third_party" / "ref_install" / "circuits" / f"{WORKLOAD}.qasm"
+    if not exe.exists() or not circuit.exists():
+        return {"unavailable": "build/flatdd_gpu or the circuit file is not present (needs `make -C third_party` where a reference checkout exists)"}
+    stats = None
+    walls = []
+    for _ in range(2):  # the first run pages the binary and the CUDA context in
+        with tempfile.TemporaryDirectory() as tmp:
+            cwd = Path(tmp) / "build" / "apps"
+            cwd.mkdir(parents=True)
+            (Path(tmp) / "log" / "results" / "time").mkdir(parents=True)
+            t0 = time.perf_counter()
+            out = subprocess.run([str(exe), "--file", str(circuit), "-t", str(threads), "--fuse", "4", "--quiet"], cwd=cwd,
+                                 capture_output=True, text=True, check=True).stdout
+            walls.append(time.perf_counter() - t0)
+            stats = json.loads(out[out.rindex('{\n  "statistics"'):])["statistics"]
+    res = {"binary": "build/flatdd_gpu --fuse 4 (parse + host DD phase + conversion + fusion pass + array phase on the GPU)",
+           "simulation_time_s": stats["simulation_time"], "process_wall_s": walls[-1], "gate_merging_s": stats["gate_merging_time"],
+           "array_phase_s": stats["array_phase_time"], "dd_to_array_s": stats["DD->Array conversion"],
+           "array_phase_launches": stats["array_phase_launches"], "applied_gates": stats["applied_gates"],
+           "gates_per_sec_whole_circuit": stats["applied_gates"] / stats["simulation_time"]}
+    man = ROOT / "bench_inputs" / "samples" / f"{WORKLOAD}.manifest.json"
+    if man.exists():
+        ref = json.loads(man.read_text()).get("reference") or {}
+        res["reference_simulate_s_recorded"] = ref.get("simulate_s")
+        res["reference_note"] = ("the unmodified reference's simulate() on this circuit, --fuse 1 -t 8, recorded when the golden samples were "
+                                 "made (not re-run here: 18 minutes)")
+    return res
+
+
+def gpu_arm(args) -> int:
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: flatdd_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    workload = args.workload
+    warmup = max(3, args.warmup)
+    main = measure(workload, args, args.steps, warmup, with_e2e=True)
+    # the north-star sharded workloads ride along at N > 1 (fewer steps: their steps are 10-100x longer)
+    extras = []
+    if args.extra == "auto":
+        names = [w for w, counts in (("knn_n31_f0", (2, 4, 8)), ("synth_n34", (8,))) if world in counts] if workload == WORKLOAD else []
     else:
-        body_mean = statistics.mean(body_ms)
+        names = [w for w in args.extra.split(",") if w and w != "none"]
+    for name in names:
+        extras.append(measure(name, args, steps=3, warmup=3, with_e2e=False))
 
     if rank == 0:
-        peaks = {}
-        peaks_file = ROOT / "MEASURED_PEAKS.json"
-        if peaks_file.exists():
-            peaks = json.loads(peaks_file.read_text())
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        # DMAVM launch time: the step body minus the exchanges
-        launch_ms = (body_mean - exch_mean_ms * n_exch) / max(1, n_gates)
-        achieved = 32.0 * local_dim / (launch_ms * 1e-3) / 1e9
-        traffic = None
-        tf = ROOT / "profiles" / "dmavm_traffic.json"
-        if tf.exists() and n_local == 26:
-            traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+        n_local = main["n_local"]
+        n_exch = main["n_exch"]
+        method = args.exchange_method
         line = {
-            "metric": METRIC, "value": array_ops / (t_step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": warmup, "ms_per_step": t_step_ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{workload} array phase: DD->array conversion + {n_gates} fused DMAVM launches "
-                                   f"({array_ops} circuit ops after the switch)" + (f" + {n_exch} half-shard exchanges" if world > 1 else ""),
-                       "n_qubits": n, "state_bytes": 16 << n, "fusion": "per gate (fuse 0)" if "_f0" in workload else "dependency-graph fusion with the GPU cost model (fuse 4)",
+            "config": {"workload": f"{workload} array phase: DD->array conversion + {main['n_gates']} fused DMAVM launches "
+                                   f"({main['array_ops']} circuit ops after the switch)" + (f" + {n_exch} half-shard exchanges" if world > 1 else ""),
+                       "n_qubits": main["n_qubits"], "state_bytes": 16 << main["n_qubits"],
+                       "fusion": "per gate (fuse 0)" if "_f0" in workload else "dependency-graph fusion with the GPU cost model (fuse 4)",
                        "parallelism": "1 GPU" if world == 1 else f"state sharded over {world} GPUs by its top {world.bit_length() - 1} qubits; "
                                       f"qubit remap + half-shard exchange ({'peer-memory kernel' if method == 0 else 'NCCL send/recv'})",
+                       "scaling_note": "the same circuit and state at every GPU count (strong scaling)",
                        "l2": f"shard ({(16 << n_local) >> 20} MiB) and its ping-pong partner exceed the 126 MB L2; no flush needed"
                              if n_local >= 24 else "shard fits L2 at this GPU count (strong scaling of a 1 GiB state)"},
-            "seconds_per_circuit": t_step_ms * 1e-3,
-            "convert_ms": statistics.mean(convert_ms), "dmavm_ms_per_launch": launch_ms,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "dmavm_tile_kernel", "peak_source": peak_src, "bytes_per_launch": 32 * local_dim,
-                         "convert_gbs": 16.0 * local_dim / (statistics.mean(convert_ms) * 1e-3) / 1e9},
-            "e2e": {"value": array_ops / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "seconds_per_circuit": e2e_s, "steps": e2e_steps},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "check": {"norm2_device": norm2, "norm2_host_copy": host_norm2},
+            "seconds_per_circuit": main["ms_per_step"] * 1e-3,
+            "convert_ms": main["convert_ms"], "dmavm_ms_per_launch": main["dmavm_ms_per_launch"],
+            "roofline": main["roofline"], "e2e": main["e2e"],
+            "gpu_launches": main["launches"], "tensor_core_launches": main["tensor_core_launches"],
+            "clocks": main["clocks"], "check": main["check"],
         }
-        if world > 1 and n_exch:
-            half_bytes = 8.0 * local_dim
-            gbs = half_bytes / (exch_mean_ms * 1e-3) / 1e9
-            line["exchange"] = {"per_step": n_exch, "bytes_each_way_per_gpu": half_bytes, "ms_mean": exch_mean_ms, "gbs_per_direction": gbs,
-                                "frac_of_nvlink_nominal_900": gbs / 900.0, "frac_of_nvlink_measured_770": gbs / 770.0,
-                                "method": "peer-memory kernel (barrier + kernel + barrier)" if method == 0 else "NCCL send/recv + D2D copy"}
+        if "exchange" in main:
+            line["exchange"] = main["exchange"]
+        if extras:
+            line["extra_workloads"] = [{k: e[k] for k in ("workload", "n_qubits", "n_gates", "n_exch", "array_ops", "value", "ms_per_step",
+                                                           "dmavm_ms_per_launch", "roofline", "check", "clocks") if k in e}
+                                       | ({"exchange": e["exchange"]} if "exchange" in e else {}) for e in extras]
         if world == 1 and not args.no_cpu and workload == WORKLOAD:
             try:
                 r = run_reference_once(host_threads())
@@ -418,8 +522,11 @@ def gpu_arm(args) -> int:
                               f"-t {host_threads()} on {os.cpu_count()} host cores"}
             except Exception as exc:  # the baseline is reported, never allowed to void the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_threads(), "kind": "reference", "sample": f"failed: {exc}"}
+            try:
+                line["circuit_wall"] = circuit_wall(host_threads())
+            except Exception as exc:
+                line["circuit_wall"] = {"unavailable": f"failed: {exc}"}
         print(json.dumps(line))
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -434,6 +541,7 @@ def main() -> int:
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default=WORKLOAD, help="supremacy_n26 (default), supremacy_n20, knn_n31_f0, ... (needs its boundary trace)")
     ap.add_argument("--exchange-method", type=int, default=0, help="0 = peer-memory kernel, 1 = NCCL send/recv")
+    ap.add_argument("--extra", default="auto", help="extra workloads timed in the same run: auto (knn_n31_f0 at 2/4/8 GPUs, synth_n34 at 8), none, or a comma list")
     ap.add_argument("--option", action="append", default=[], help="experiments: library tunable key=value (fdd_set_option), repeatable")
     args = ap.parse_args()
     if args.impl == "reference":

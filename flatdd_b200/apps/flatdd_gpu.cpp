@@ -4,7 +4,10 @@
 // ../../log/results/{time,state}/<name>_FlatDD.txt files.  The array phase runs on the GPU through
 // the C-ABI (include/flatdd_b200.h).  Additions: --gpu D (device), --fuse 3 / 4 (GPU cost model: greedy in program order / dependency graph),
 // --bin FILE (final state as raw little-endian fp64: real array then imag array), --trace FILE
-// (also record the boundary traffic), --quiet.
+// (also record the boundary traffic), --trace-only (record the boundary traffic WITHOUT a device: the host DD phase,
+// the switch rule and the fusion pass run, every flat table that would cross the C-ABI goes to the --trace file; with
+// --world N the schedule carries the half-shard exchanges of an N-shard state.  This is how the inputs of bench.py
+// are made where no GPU exists), --quiet.
 // Multi-GPU: start one process per GPU with --world N --rank r --rendezvous FILE (rank 0 writes the
 // NCCL unique id there, the others wait for it); every rank runs the same driver on the same circuit,
 // holds the shard with top index bits r and writes it to <--bin>.rank<r>.
@@ -39,6 +42,7 @@ int main(int argc, char** argv) {
         ("gpu", "CUDA device", cxxopts::value<int>()->default_value("0"))
         ("bin", "write the final state as raw fp64 (re[], im[])", cxxopts::value<std::string>())
         ("trace", "record the boundary traffic to this file", cxxopts::value<std::string>())
+        ("trace-only", "no device: only record the boundary traffic (needs --trace; with --world N the N-shard schedule)")
         ("world", "number of shards / processes (power of two)", cxxopts::value<int>()->default_value("1"))
         ("rank", "rank of this process", cxxopts::value<int>()->default_value("0"))
         ("rendezvous", "file through which rank 0 hands out the NCCL unique id", cxxopts::value<std::string>()->default_value(""))
@@ -60,9 +64,16 @@ int main(int argc, char** argv) {
 
     const int world = vm["world"].as<int>();
     const int rank = vm["rank"].as<int>();
+    const bool traceOnly = vm.count("trace-only") > 0;
+    if (traceOnly && vm.count("trace") == 0) {
+        std::cerr << "flatdd_gpu: --trace-only needs --trace FILE\n";
+        return 1;
+    }
     std::unique_ptr<fddb200::GpuArrayBackend> gpu;
     try {
-        if (world > 1) {
+        if (traceOnly) {
+            // no device is touched; nothing is computed
+        } else if (world > 1) {
             const std::string rendezvous = vm["rendezvous"].as<std::string>();
             if (rendezvous.empty()) throw std::runtime_error("--world needs --rendezvous FILE");
             char id[128];
@@ -94,10 +105,15 @@ int main(int argc, char** argv) {
     fddb200::ArrayBackend* backend = gpu.get();
     if (vm.count("trace") > 0) {
         recorder = std::make_unique<fddb200::TraceRecorder>(vm["trace"].as<std::string>(), nQubits);
-        tee = std::make_unique<fddb200::TeeBackend>(std::vector<fddb200::ArrayBackend*>{gpu.get(), recorder.get()});
-        backend = tee.get();
+        if (traceOnly) {
+            if (world > 1) recorder->setWorldSize(world);
+            backend = recorder.get();
+        } else {
+            tee = std::make_unique<fddb200::TeeBackend>(std::vector<fddb200::ArrayBackend*>{gpu.get(), recorder.get()});
+            backend = tee.get();
+        }
     }
-    if (vm.count("time-gates") > 0) gpu->setTiming(true);
+    if (vm.count("time-gates") > 0 && gpu) gpu->setTiming(true);
     fddb200::RefGpuSwitchSimulator sim(std::move(circuit), backend);
     sim.threshold = vm["thresh"].as<double>();
     const auto nThread = vm["t"].as<unsigned int>();
@@ -113,6 +129,18 @@ int main(int argc, char** argv) {
     const std::chrono::duration<float> durationSimulation = t2 - t1;
     std::cout << "Simulation finished" << std::endl;
 
+    if (traceOnly) {
+        if (!sim.switched) sim.getVectorFromDD(); // what --pv / getVector would convert (apps/FlatDD.cpp:89-93)
+        recorder->close();
+        nlohmann::json traced;
+        traced["trace"] = {{"file", vm["trace"].as<std::string>()}, {"records", recorder->records()}, {"n_qubits", nQubits},
+                           {"n_ops", sim.getNumberOfOps()}, {"switched", sim.switched}, {"switched_at_op", sim.switchedAtOp},
+                           {"unitary_ops", sim.unitaryOps}, {"array_phase_ops", sim.arrayPhaseOps}, {"launches", sim.launches},
+                           {"world", world}, {"exchanges", sim.exchanges}, {"fuse", sim.fuse}, {"gate_merging_s", sim.gateMergingTime},
+                           {"simulation_time", durationSimulation.count()}};
+        std::cout << std::setw(2) << traced << std::endl;
+        return 0;
+    }
     if (vm.count("pv") > 0 || vm.count("bin") > 0) {
         double* re = nullptr;
         double* im = nullptr;

@@ -30,7 +30,7 @@ EXPORTS = [
     "fdd_exchange_qubits", "fdd_relabel_qubits", "fdd_barrier",
     "fdd_convert", "fdd_apply", "fdd_gate_compile", "fdd_gate_apply", "fdd_gate_apply_many", "fdd_gate_free", "fdd_gate_info",
     "fdd_ddarr_multiply", "fdd_mac_count", "fdd_cost_ip", "fdd_cost_op1", "fdd_cost_gpu", "fdd_matdd_info", "fdd_get_state",
-    "fdd_set_state", "fdd_set_zero_state", "fdd_get_amplitudes", "fdd_norm2", "fdd_sample", "fdd_state_device_ptr",
+    "fdd_set_state", "fdd_set_zero_state", "fdd_get_amplitudes", "fdd_get_amplitudes_at", "fdd_norm2", "fdd_sample", "fdd_state_device_ptr",
     "fdd_get_permutation", "fdd_canonicalize", "fdd_last_kernel_ms", "fdd_set_timing", "fdd_launch_count", "fdd_stream",
 ]
 
@@ -81,6 +81,7 @@ class Library:
         L.fdd_set_state.argtypes = [vp, dp, dp]
         L.fdd_set_zero_state.argtypes = [vp]
         L.fdd_get_amplitudes.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint64, dp]
+        L.fdd_get_amplitudes_at.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), ctypes.c_uint64, dp]
         L.fdd_norm2.argtypes = [vp, dp]
         L.fdd_sample.argtypes = [vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]
         L.fdd_state_device_ptr.argtypes = [vp, ctypes.POINTER(vp)]
@@ -293,6 +294,14 @@ class Context:
     def get_amplitudes(self, first: int, count: int) -> np.ndarray:
         out = np.empty(2 * count, dtype=np.float64)
         self.L.check(self.L.lib.fdd_get_amplitudes(self._h, first, count, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+        return out.view(np.complex128)
+
+    def get_amplitudes_at(self, local_indices) -> np.ndarray:
+        """Amplitudes at arbitrary local indices, gathered on the device."""
+        idx = np.ascontiguousarray(local_indices, dtype=np.uint64)
+        out = np.empty(2 * idx.size, dtype=np.float64)
+        self.L.check(self.L.lib.fdd_get_amplitudes_at(self._h, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), idx.size,
+                                                      out.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
         return out.view(np.complex128)
 
     def norm2(self) -> float:

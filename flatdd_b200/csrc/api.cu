@@ -1046,6 +1046,30 @@ int fdd_get_amplitudes(fdd_ctx* ctx, uint64_t first, uint64_t count, double* int
     });
 }
 
+int fdd_get_amplitudes_at(fdd_ctx* ctx, const uint64_t* local_indices, uint64_t count, double* interleaved) {
+    return guarded([&] {
+        if (ctx == nullptr || (count > 0 && (local_indices == nullptr || interleaved == nullptr))) throw std::invalid_argument("null argument");
+        if (!ctx->hasState) throw std::logic_error("no state");
+        if (count == 0) return;
+        for (uint64_t i = 0; i < count; ++i) {
+            if (local_indices[i] >= ctx->localDim()) throw std::invalid_argument("amplitude index out of bounds");
+        }
+        useDevice(ctx);
+        uint64_t* dIdx = nullptr;
+        double2* dOut = nullptr;
+        CUDA_TRY(cudaMallocAsync(&dIdx, sizeof(uint64_t) * count, ctx->stream));
+        CUDA_TRY(cudaMallocAsync(&dOut, sizeof(double2) * count, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(dIdx, local_indices, sizeof(uint64_t) * count, cudaMemcpyHostToDevice, ctx->stream));
+        gather_kernel<<<static_cast<unsigned>((count + 255) / 256), 256, 0, ctx->stream>>>(ctx->buf[ctx->cur], dIdx, count, dOut);
+        CUDA_TRY(cudaGetLastError());
+        ctx->launches++;
+        CUDA_TRY(cudaMemcpyAsync(interleaved, dOut, sizeof(double2) * count, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaFreeAsync(dIdx, ctx->stream));
+        CUDA_TRY(cudaFreeAsync(dOut, ctx->stream));
+    });
+}
+
 int fdd_norm2(fdd_ctx* ctx, double* out) {
     return guarded([&] {
         if (ctx == nullptr || out == nullptr) throw std::invalid_argument("null argument");

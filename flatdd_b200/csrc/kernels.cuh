@@ -1300,6 +1300,11 @@ __global__ void zero_state_kernel(double2* out, uint64_t n, int setOne) {
         out[i] = make_double2((i == 0 && setOne) ? 1.0 : 0.0, 0.0);
     }
 }
+// amplitudes at arbitrary indices (sampled comparison of large states)
+__global__ void gather_kernel(const double2* __restrict__ in, const uint64_t* __restrict__ idx, uint64_t count, double2* __restrict__ out) {
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = in[idx[i]];
+}
 // ---- measurement sampling ---------------------------------------------------------------------------
 // probability mass of every block of `blockAmps` consecutive amplitudes (one CTA per block, fixed order)
 __global__ void __launch_bounds__(256) block_mass_kernel(const double2* __restrict__ in, uint64_t n, uint32_t blockAmps, double* __restrict__ mass) {

@@ -135,8 +135,12 @@ class TraceRecord:
 
 
 def read_trace(path) -> tuple[int, List[TraceRecord]]:
-    """Boundary trace (TraceRecorder): returns (n_qubits, records)."""
-    buf = memoryview(Path(path).read_bytes())
+    """Boundary trace (TraceRecorder), raw or gzip'd (*.gz): returns (n_qubits, records)."""
+    raw = Path(path).read_bytes()
+    if raw[:2] == b"\x1f\x8b":
+        import gzip
+        raw = gzip.decompress(raw)
+    buf = memoryview(raw)
     if bytes(buf[:8]) != b"FDDTRC01":
         raise ValueError(f"{path}: not a flatdd_b200 trace")
     n_qubits, n_records = struct.unpack_from("<2i", buf, 8)

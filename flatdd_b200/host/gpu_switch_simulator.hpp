@@ -410,12 +410,20 @@ private:
         bool cache = false;
     };
 
-    Cost referenceCost(const MEdge& g, std::unordered_map<decltype(g.p), std::size_t>& macMap, std::size_t nDim) {
+    // The reference's own prices (DMAVMACStatIP / DMAVMACStatOP1, include/dd/SwitchPackage.hpp:3006-3017) computed by the
+    // library on the flat table (fdd_cost_ip / fdd_cost_op1: the same integers, tests/test_library_host.py).
+    Cost referenceCost(const MEdge& g) {
         Cost c;
-        c.ip = dd->DMAVMACStatIP(g, macMap, nDim, n_thread_exp);
-        const std::size_t op1 = dd->DMAVMACStatOP1(g, macMap, nDim, n_thread_exp);
-        c.cache = !(c.ip < op1);
-        c.value = c.cache ? op1 : c.ip;
+        const auto flat = flatten<4, MEdge, WeightTraits>(g, nq());
+        const fdd_matdd m = view(flat);
+        uint64_t ip = 0, op1 = 0;
+        // (more threads than amplitudes has no meaning in the reference either: its segment size becomes 0)
+        const unsigned tExp = std::min<unsigned>(n_thread_exp, static_cast<unsigned>(nq() - 1));
+        fddCheck(fdd_cost_ip(&m, tExp, &ip), "fdd_cost_ip");
+        fddCheck(fdd_cost_op1(&m, tExp, &op1), "fdd_cost_op1");
+        c.ip = static_cast<std::size_t>(ip);
+        c.cache = !(ip < op1);
+        c.value = static_cast<std::size_t>(c.cache ? op1 : ip);
         return c;
     }
 
@@ -443,7 +451,6 @@ private:
     Schedule buildSchedule(std::size_t first) {
         if (fuse == 4) return buildScheduleDag(first);
         Schedule s;
-        const std::size_t nDim = std::size_t{1} << qc->getNqubits();
         const auto& ops = qc->ops;
         auto current = dd->makeIdent(qc->getNqubits());
         int currentCount = 0;
@@ -480,7 +487,6 @@ private:
         if (verbose) {
             std::cout << (fuse == 1 ? "Using greedy merge... " : "Using GPU-cost greedy merge... ") << std::endl;
         }
-        std::unordered_map<decltype(current.p), std::size_t> macMap;
         Cost held; // cost of `current`
         std::size_t totalComp = 0;
         std::size_t savedComp = 0;
@@ -494,12 +500,11 @@ private:
                 current = dd->makeIdent(qc->getNqubits());
                 currentCount = 0;
                 held = Cost{};
-                macMap.clear();
             }
             auto next = gateFor(ops[k].get(), &s.pending);
-            const Cost nextCost = fuse == 1 ? referenceCost(next, macMap, nDim) : gpuCost(next);
+            const Cost nextCost = fuse == 1 ? referenceCost(next) : gpuCost(next);
             auto candidate = dd->multiply(next, current);
-            const Cost mergedCost = fuse == 1 ? referenceCost(candidate, macMap, nDim) : gpuCost(candidate);
+            const Cost mergedCost = fuse == 1 ? referenceCost(candidate) : gpuCost(candidate);
             const bool lastOp = k == ops.size() - 1 || ops[k + 1]->isNonUnitaryOperation();
             if (held.value + nextCost.value < mergedCost.value || lastOp) {
                 s.push(current, currentCount, held.cache);
@@ -508,7 +513,6 @@ private:
                 held = nextCost;
                 current = next;
                 currentCount = 1;
-                macMap.clear();
             } else {
                 current = candidate;
                 ++currentCount;

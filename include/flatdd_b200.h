@@ -182,6 +182,10 @@ int fdd_set_state(fdd_ctx* ctx, const double* real, const double* imag);
 int fdd_set_zero_state(fdd_ctx* ctx);
 /* Read `count` amplitudes starting at local index `first` (interleaved re,im pairs). */
 int fdd_get_amplitudes(fdd_ctx* ctx, uint64_t first, uint64_t count, double* interleaved);
+/* Read the amplitudes at `count` arbitrary LOCAL indices (interleaved re,im pairs), gathered on the device: the sampled
+ * comparison of states that are too large to download (reference getVector, include/SwitchSimulator.hpp:55-63, read at a
+ * few indices).  Sharded states: local index = global index without the top log2(world) bits, valid after fdd_canonicalize. */
+int fdd_get_amplitudes_at(fdd_ctx* ctx, const uint64_t* local_indices, uint64_t count, double* interleaved);
 /* sum |amp|^2 over the local shard, computed on the device. */
 int fdd_norm2(fdd_ctx* ctx, double* out);
 /* Measurement sampling on the device (the reference skips measurements,

@@ -7,7 +7,7 @@
     python oracle/make_golden.py traces    # boundary traces of the bench circuits (no reference run)
     python oracle/make_golden.py samples   # truncated circuits for the bounded CPU-baseline runs
     python oracle/make_golden.py circuits  # copy the reference's 12 circuits next to the binaries (git-ignored)
-    python oracle/make_golden.py pack      # gzip the bench trace into tests/golden/traces/ (committed)
+    python oracle/make_golden.py publish   # copy the reference's sampled amplitudes of the bench workloads to bench_inputs/samples/ (committed)
 
 Needs /root/reference (for `make -C oracle ref`) and the repo's own test circuits."""
 from __future__ import annotations
@@ -43,7 +43,7 @@ SMALL = {
     "compound_n9_f1": ("tests/circuits/compound_n9.qasm", 4, 1, ["--kat-gates", "1"]),
 }
 MEDIUM = {
-    "synth_n20_f1": (ROOT / "oracle/_ref/circuits/synth_n20.qasm", 8, 1, ["--no-kat", "--samples", "65536"]),
+    "synth_n20_f1": (ROOT / "bench_inputs/circuits/synth_n20.qasm", 8, 1, ["--no-kat", "--samples", "65536"]),
     "vqe_n16_f0": (REF / "circuits/vqe_n16.qasm", 8, 0, ["--no-kat", "--full-state"]),
     "vqe_n16_f1": (REF / "circuits/vqe_n16.qasm", 8, 1, ["--no-kat", "--full-state"]),
     "dnn_n16_f1": (REF / "circuits/dnn_n16.qasm", 8, 1, ["--no-kat", "--full-state"]),
@@ -87,14 +87,14 @@ TRACES = {
     "supremacy_n26_gpu_w8": (REF / "circuits/supremacy_n26.qasm", 4, 8),
     "supremacy_n20_gpu_w2": (REF / "circuits/supremacy_n20.qasm", 4, 2),
     "knn_n25_f0_w2": (REF / "circuits/knn_n25.qasm", 0, 2),
-    "synth_n26_w1": (ROOT / "oracle/_ref/circuits/synth_n26.qasm", 4, 1),
-    "synth_n26_w8": (ROOT / "oracle/_ref/circuits/synth_n26.qasm", 4, 8),
-    "synth_n30_w1": (ROOT / "oracle/_ref/circuits/synth_n30.qasm", 4, 1),
-    "synth_n30_w2": (ROOT / "oracle/_ref/circuits/synth_n30.qasm", 4, 2),
-    "synth_n30_w4": (ROOT / "oracle/_ref/circuits/synth_n30.qasm", 4, 4),
-    "synth_n30_w8": (ROOT / "oracle/_ref/circuits/synth_n30.qasm", 4, 8),
-    "synth_n34_w8": (ROOT / "oracle/_ref/circuits/synth_n34.qasm", 4, 8),
-    "synth_n20_w2": (ROOT / "oracle/_ref/circuits/synth_n20.qasm", 4, 2),
+    "synth_n26_w1": (ROOT / "bench_inputs/circuits/synth_n26.qasm", 4, 1),
+    "synth_n26_w8": (ROOT / "bench_inputs/circuits/synth_n26.qasm", 4, 8),
+    "synth_n30_w1": (ROOT / "bench_inputs/circuits/synth_n30.qasm", 4, 1),
+    "synth_n30_w2": (ROOT / "bench_inputs/circuits/synth_n30.qasm", 4, 2),
+    "synth_n30_w4": (ROOT / "bench_inputs/circuits/synth_n30.qasm", 4, 4),
+    "synth_n30_w8": (ROOT / "bench_inputs/circuits/synth_n30.qasm", 4, 8),
+    "synth_n34_w8": (ROOT / "bench_inputs/circuits/synth_n34.qasm", 4, 8),
+    "synth_n20_w2": (ROOT / "bench_inputs/circuits/synth_n20.qasm", 4, 2),
     "knn_n31_f0_w1": (REF / "circuits/knn_n31.qasm", 0, 1),
     "knn_n31_f0_w2": (REF / "circuits/knn_n31.qasm", 0, 2),
     "knn_n31_f0_w4": (REF / "circuits/knn_n31.qasm", 0, 4),
@@ -151,15 +151,17 @@ def main(argv):
         dst.mkdir(parents=True, exist_ok=True)
         for q in sorted((REF / "circuits").glob("*.qasm")):
             shutil.copyfile(q, dst / q.name)
-    elif what == "pack":
-        import gzip
+    elif what == "publish":
+        # the reference's sampled final amplitudes of the workloads bench.py runs: bench.py compares its own final
+        # state with them at every GPU count (check.max_amp_err_vs_reference)
         import shutil
-        dst = ROOT / "tests" / "golden" / "traces"
+        dst = ROOT / "bench_inputs" / "samples"
         dst.mkdir(parents=True, exist_ok=True)
-        for name in only or ["supremacy_n26_gpu"]:
-            with open(ROOT / "oracle" / "_ref" / "traces" / name / "trace.bin", "rb") as src, \
-                    gzip.GzipFile(dst / f"{name}.trace.gz", "wb", compresslevel=9, mtime=0) as out:
-                shutil.copyfileobj(src, out)
+        for workload, case in (("supremacy_n26", "supremacy_n26_f1"), ("knn_n31_f0", "knn_n31_f0")):
+            src = ROOT / "oracle" / "_ref" / "golden" / case
+            if (src / "samples.bin").exists():
+                shutil.copyfile(src / "samples.bin", dst / f"{workload}.samples.bin")
+                shutil.copyfile(src / "manifest.json", dst / f"{workload}.manifest.json")
     else:
         raise SystemExit(__doc__)
 

@@ -48,7 +48,7 @@ def test_trace_replay(case):
 @pytest.mark.parametrize("case", TRAVEL_CASES)
 def test_cli_gpu_fusion(case, fuse):
     m = G.manifest(case, G.TRAVEL)
-    circuit = ROOT / "oracle" / "_ref" / "circuits" / m["circuit"]
+    circuit = G.circuit_path(m["circuit"])
     if not circuit.exists():
         pytest.skip(f"{circuit} not present")
     out, stats, re, im, _ = run_cli(circuit, 16, fuse, extra=("--quiet",))

@@ -53,7 +53,7 @@ TRAVEL = [c for c in G.cases(G.TRAVEL)]
 def test_standalone_on_reference_circuits(case):
     """The reference's own circuits (golden data written by the compiled reference, oracle/_ref/golden)."""
     m = G.manifest(case, G.TRAVEL)
-    circuit = ROOT / "oracle" / "_ref" / "circuits" / m["circuit"]
+    circuit = G.circuit_path(m["circuit"])
     if not circuit.exists():
         pytest.skip(f"{circuit} not present")
     full, re, im = run(circuit, 2, extra=("--time-gates",))

@@ -1,5 +1,5 @@
 """Runs build/flatdd_gpu (or, with `standalone` as second argument, build/flatdd_gpu_standalone) on every reference
-circuit present under oracle/_ref/circuits and prints one JSON line per circuit (the CLI's own statistics block).
+circuit present under third_party/ref_install/circuits and prints one JSON line per circuit (the CLI's own statistics block).
 usage: python tools/run_all_circuits.py [fuse] [standalone|dd] [time-gates]
 (time-gates synchronises after every launch to report per-launch device time; array_phase_time is then not representative)"""
 import json
@@ -16,7 +16,7 @@ fuse = sys.argv[1] if len(sys.argv) > 1 else ("2" if standalone else "4")
 names = ["ghz_state_n23", "vqe_n16", "dnn_n16", "dnn_n20", "supremacy_n20", "supremacy_n24", "knn_n25", "swap_test_n25", "dnn_n25",
          "supremacy_n26", "adder_n28", "knn_n31"]
 for name in names:
-    circuit = ROOT / "oracle" / "_ref" / "circuits" / f"{name}.qasm"
+    circuit = ROOT / "third_party" / "ref_install" / "circuits" / f"{name}.qasm"
     if not circuit.exists():
         continue
     with tempfile.TemporaryDirectory() as tmp:
