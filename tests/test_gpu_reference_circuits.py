@@ -39,8 +39,29 @@ def test_trace_replay(case):
     with Context(n) as ctx:
         for rec in records:
             (ctx.convert if rec.kind == 1 else ctx.apply)(rec.dd)
+        if n >= 30:
+            # knn_n31 (32 GiB): the reference's sampled amplitudes are gathered on the device, the norm is computed there
+            m = G.manifest(case, G.TRAVEL)
+            idx, sr, si = G.samples(case, G.TRAVEL)
+            got = ctx.get_amplitudes_at(idx)
+            assert float(np.max(np.abs(got - (sr + 1j * si)))) < AMP_TOL
+            assert abs(ctx.norm2() - m["reference"]["norm2"]) < 1e-9
+            return
         re, im = ctx.get_state()
     _check(case, re, im)
+
+
+def test_get_amplitudes_at_matches_the_downloaded_state():
+    n, records = read_trace(ROOT / "tests" / "golden" / "mix_n10_f1" / "trace.bin")
+    with Context(n) as ctx:
+        for rec in records:
+            (ctx.convert if rec.kind == 1 else ctx.apply)(rec.dd)
+        re, im = ctx.get_state()
+        idx = np.array([0, 1, 5, 1023, 512, 77, 77], dtype=np.uint64)
+        got = ctx.get_amplitudes_at(idx)
+        assert np.array_equal(got, re[idx.astype(np.int64)] + 1j * im[idx.astype(np.int64)])
+        with pytest.raises(Exception):
+            ctx.get_amplitudes_at(np.array([1 << n], dtype=np.uint64))
 
 
 @pytest.mark.skipif(not CLI.exists(), reason="build/flatdd_gpu not built")
@@ -51,6 +72,8 @@ def test_cli_gpu_fusion(case, fuse):
     circuit = G.circuit_path(m["circuit"])
     if not circuit.exists():
         pytest.skip(f"{circuit} not present")
+    if m["n_qubits"] >= 30:
+        pytest.skip("the CLI route writes the whole state to disk (32 GiB at n = 31); knn_n31 is covered by the trace replay and by bench.py's check")
     out, stats, re, im, _ = run_cli(circuit, 16, fuse, extra=("--quiet",))
     assert stats["switched"] == m["reference"]["switched"]
     _check(case, re, im)
