@@ -123,6 +123,7 @@ int main(int argc, char** argv) {
     sim.ddsim_convert = vm.count("DDSIM_convert") > 0;
     sim.verbose = vm.count("quiet") == 0 && rank == 0;
     sim.worldSize = world;
+    sim.timePerGate = vm.count("time-gates") > 0;
 
     sim.simulate();
     const auto t2 = std::chrono::high_resolution_clock::now();

@@ -28,7 +28,7 @@ EXPORTS = [
     "fdd_version", "fdd_last_error", "fdd_device_count", "fdd_create", "fdd_create_sharded", "fdd_destroy",
     "fdd_n_qubits", "fdd_n_local_qubits", "fdd_synchronize", "fdd_set_option", "fdd_get_option", "fdd_comm_unique_id", "fdd_comm_init",
     "fdd_exchange_qubits", "fdd_relabel_qubits", "fdd_barrier",
-    "fdd_convert", "fdd_apply", "fdd_gate_compile", "fdd_gate_apply", "fdd_gate_apply_many", "fdd_gate_free", "fdd_gate_info",
+    "fdd_convert", "fdd_apply", "fdd_apply_many", "fdd_gate_compile", "fdd_gate_apply", "fdd_gate_apply_many", "fdd_gate_free", "fdd_gate_info",
     "fdd_ddarr_multiply", "fdd_mac_count", "fdd_cost_ip", "fdd_cost_op1", "fdd_cost_gpu", "fdd_matdd_info", "fdd_get_state",
     "fdd_set_state", "fdd_set_zero_state", "fdd_get_amplitudes", "fdd_get_amplitudes_at", "fdd_norm2", "fdd_sample", "fdd_state_device_ptr",
     "fdd_get_permutation", "fdd_canonicalize", "fdd_last_kernel_ms", "fdd_set_timing", "fdd_launch_count", "fdd_stream",
@@ -65,6 +65,7 @@ class Library:
         L.fdd_barrier.argtypes = [vp]
         L.fdd_convert.argtypes = [vp, ddp]
         L.fdd_apply.argtypes = [vp, ddp]
+        L.fdd_apply_many.argtypes = [vp, ddp, i32]
         L.fdd_gate_compile.argtypes = [vp, ddp, ctypes.POINTER(vp)]
         L.fdd_gate_apply.argtypes = [vp, vp]
         L.fdd_gate_apply_many.argtypes = [vp, ctypes.POINTER(vp), i32]
@@ -253,6 +254,14 @@ class Context:
     def apply(self, gate: FlatDD):
         c = gate.as_c()
         self.L.check(self.L.lib.fdd_apply(self._h, ctypes.byref(c)))
+
+    def apply_many(self, gates):
+        """Host tables of several gates in one boundary call: dense blocks among them share passes over the state."""
+        gates = list(gates)
+        if not gates:
+            return
+        arr = (type(gates[0].as_c()) * len(gates))(*[g.as_c() for g in gates])
+        self.L.check(self.L.lib.fdd_apply_many(self._h, arr, len(gates)))
 
     def compile(self, gate: FlatDD) -> CompiledGate:
         c = gate.as_c()

@@ -4,6 +4,8 @@
 #include "gate_compile.hpp"
 #include "kernels.cuh"
 #include "comm.cuh"
+#include "block_compile.hpp"
+#include "block_kernel.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -11,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <tuple>
 #include <string>
@@ -81,6 +84,11 @@ struct fdd_gate {
     uint8_t* dSubFlags = nullptr;
     void* dBlob = nullptr; // one allocation holding all of the above
     mutable double2* dCtx = nullptr; // tensor-core path: blocks of a non-uniform gate per value of its context bits (built at the first launch)
+    // dense-block path (block_kernel.cuh): the gate as a 2^k x 2^k block with its context table, when it is one
+    std::unique_ptr<DenseBlock> block;
+    double* dTable = nullptr;
+    uint64_t serial = 0; // identifies the gate in the plan cache (pointers are reused by the allocator)
+    const fdd_matdd* source = nullptr; // fdd_apply_many only: the caller's table while the call runs (lazy tables for the older kernels)
 };
 
 struct fdd_ctx {
@@ -115,6 +123,27 @@ struct fdd_ctx {
     int dmma = 1;         // dense upper blocks of 8 / 16 segments on the FP64 tensor cores (tile kernel MODE 5); 0: CUDA-core FMAs
     int exchangeUnroll = 8;
     int exchangeCtasPerSm = 4;
+    int blockKernel = 1;      // gates that are dense blocks (<= 4 non-diagonal qubits anywhere, <= 10 context qubits) take the tile-resident kernel
+    int blockTileBits = 12;   // preferred tile size of a pass (log2 amplitudes); grows to 13 when the blocks of a pass need it
+    int blockMaxPerPass = kPassMaxBlocks; // 1: one pass per block (A/B against the fused passes)
+    int blockWarps = 0;       // experiments: 16 = sixteen warps per CTA with one unit per iteration
+    int blockUnits = 2;       // units per iteration and warp (2: twelve independent tensor-core chains, one CTA per SM; 1: two CTAs per SM)
+    int blockBuffers = 3;     // tile buffers per CTA when they fit (copy-in, tensor-core work and copy-out of consecutive tiles overlap)
+    int blockWs = 1;          // warp-specialised kernel (memory warps + compute warps); 0: every warp loads, computes and stores in turn
+    uint64_t blockLaunches = 0;
+    uint64_t blocksApplied = 0;
+    uint64_t gateSerial = 0;
+    struct PlannedPass {
+        PassParams params;
+        int maxUnits = 0;
+        int nBuffers = 1;
+        int warps = 8;
+        int unitsPerIter = 2;
+        bool ws = true;
+        int grid = 0;
+        size_t smem = 0;
+    };
+    std::map<std::vector<uint64_t>, PlannedPass> passPlans;
     // scratch
     double* dPartial = nullptr;
     double* dNorm = nullptr;
@@ -477,7 +506,209 @@ void freeGate(fdd_gate* g, cudaStream_t stream) {
             cudaFree(g->dBlob);
         }
     }
+    if (g->dTable != nullptr) {
+        cudaSetDevice(g->device);
+        if (stream != nullptr) {
+            cudaFreeAsync(g->dTable, stream);
+        } else {
+            cudaFree(g->dTable);
+        }
+    }
     delete g;
+}
+
+// ---- dense-block path -------------------------------------------------------------------------------------------
+// The gate as a dense block, padded to the kernel's shapes, with its table on the device; leaves g->block empty when the
+// gate is not a block (more than four non-diagonal qubits, too many context qubits, a non-local target, a tiny register).
+void attachBlock(fdd_ctx* c, fdd_gate* g, const fdd_matdd& dd) {
+    if (!c->blockKernel || c->variant != 2 || c->nLocal < 8) return;
+    auto blk = std::make_unique<DenseBlock>();
+    if (!denseBlockFromDD(dd, *blk)) return;
+    for (int q : blk->targets) {
+        if (q >= c->nLocal) return; // non-diagonal on a global qubit: the caller has to exchange first (launchWalk reports it)
+    }
+    padBlock(*blk, c->nLocal);
+    const DenseBlock* one = blk.get();
+    if (minTileBits(&one, 1, c->nLocal) < 0) return;
+    const size_t bytes = blk->table.size() * sizeof(double);
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&g->dTable), bytes, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(g->dTable, blk->table.data(), bytes, cudaMemcpyHostToDevice, c->stream)); // pageable: staged before the call returns
+    g->block = std::move(blk);
+    g->serial = ++c->gateSerial;
+}
+
+// (dmavm_variant != 2 asks for one of the older kernels explicitly)
+bool usesBlockPath(const fdd_ctx* c, const fdd_gate* g) { return c->blockKernel && c->variant == 2 && g->block != nullptr && g->dTable != nullptr; }
+
+// One pass of the tile-resident kernel over gates[0..count) (all of them blocks).  Returns false when they do not fit one
+// tile or the fragment shape cannot be planned; nothing has been launched then.
+bool launchPass(fdd_ctx* c, const fdd_gate* const* gates, int count, bool cachePlan) {
+    if (!c->hasState) throw std::logic_error("no state: call fdd_convert / fdd_set_state / fdd_set_zero_state first");
+    std::vector<uint64_t> key;
+    if (cachePlan) {
+        key.reserve(static_cast<size_t>(count) + 1);
+        key.push_back(static_cast<uint64_t>(c->blockTileBits) | (static_cast<uint64_t>(c->blockBuffers) << 8) | (static_cast<uint64_t>(c->blockWarps) << 16) | (static_cast<uint64_t>(c->blockUnits) << 24) | (static_cast<uint64_t>(c->blockWs) << 28));
+        for (int i = 0; i < count; ++i) key.push_back(gates[i]->serial);
+    }
+    fdd_ctx::PlannedPass planned;
+    const auto hit = cachePlan ? c->passPlans.find(key) : c->passPlans.end();
+    if (hit != c->passPlans.end()) {
+        planned = hit->second;
+    } else {
+        std::vector<const DenseBlock*> blocks(static_cast<size_t>(count));
+        for (int i = 0; i < count; ++i) {
+            if (gates[i]->block->n != c->n) throw std::invalid_argument("gate and context differ in the number of qubits");
+            blocks[static_cast<size_t>(i)] = gates[i]->block.get();
+        }
+        const int need = minTileBits(blocks.data(), count, c->nLocal);
+        const int maxBits = std::min(c->nLocal, kPassMaxTileBits);
+        if (need < 0 || need > maxBits) return false;
+        // preferred tile size, larger when the blocks need it or when a fragment shape cannot be planned (too few free tile bits)
+        int tileBits = std::max(need, std::min(c->blockTileBits, maxBits));
+        while (tileBits <= maxBits && !planPass(blocks.data(), count, c->nLocal, c->rank, tileBits, planned.params)) ++tileBits;
+        if (tileBits > maxBits) return false;
+        for (int i = 0; i < count; ++i) {
+            planned.params.blocks[i].table = gates[i]->dTable;
+            planned.maxUnits = std::max(planned.maxUnits, planned.params.blocks[i].nUnits);
+        }
+        planned.ws = c->blockWs != 0;
+        if (planned.ws) {
+            // warp-specialised kernel: as many tile buffers as fit (three keep copy-in, tensor work and copy-out in flight)
+            planned.grid = static_cast<int>(std::min<uint64_t>(planned.params.nTiles, static_cast<uint64_t>(c->smCount)));
+            const uint32_t tilesPerCta = (planned.params.nTiles + static_cast<uint32_t>(planned.grid) - 1) / static_cast<uint32_t>(planned.grid);
+            planned.nBuffers = 1;
+            for (int nb = std::min(3, std::max(1, c->blockBuffers)); nb >= 1; --nb) {
+                if (blockPassSmemWs(planned.params.tileBits, nb, count, planned.maxUnits, tilesPerCta) <= kSmemBudget) {
+                    planned.nBuffers = nb;
+                    break;
+                }
+            }
+            planned.smem = blockPassSmemWs(planned.params.tileBits, planned.nBuffers, count, planned.maxUnits, tilesPerCta);
+            if (planned.smem > kSmemBudget) return false;
+            static bool wsAttr = false;
+            if (!wsAttr) {
+                CUDA_TRY(cudaFuncSetAttribute(dmavm_block_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
+                wsAttr = true;
+            }
+            planned.warps = kComputeWarps + kMemoryWarps;
+        } else {
+        planned.nBuffers = (c->blockBuffers >= 2 && blockPassSmem(planned.params.tileBits, 2, count, planned.maxUnits) <= kSmemBudget) ? 2 : 1;
+        planned.smem = blockPassSmem(planned.params.tileBits, planned.nBuffers, count, planned.maxUnits);
+        if (planned.smem > kSmemBudget) return false;
+        // one CTA per SM: 8 warps, two units per iteration (12 independent tensor-core chains per warp, up to 255 registers);
+        // block_warps = 16: 16 warps with one unit per iteration; block_warps = 8 and block_units = 1: two CTAs per SM
+        planned.warps = c->blockWarps == 16 ? 16 : 8;
+        planned.unitsPerIter = (planned.warps == 8 && c->blockUnits != 1) ? 2 : 1;
+        using BlockKernel = void (*)(const PassParams, int, int);
+        const BlockKernel kernel = planned.warps == 16 ? dmavm_block_kernel<16, 1> : (planned.unitsPerIter == 2 ? dmavm_block_kernel<8, 2> : dmavm_block_kernel<8, 1>);
+        static bool attrSet = false;
+        if (!attrSet) {
+            CUDA_TRY(cudaFuncSetAttribute(dmavm_block_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
+            CUDA_TRY(cudaFuncSetAttribute(dmavm_block_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
+            CUDA_TRY(cudaFuncSetAttribute(dmavm_block_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
+            attrSet = true;
+        }
+        int resident = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, 32 * planned.warps, planned.smem));
+        if (resident < 1) return false;
+        planned.grid = static_cast<int>(std::min<uint64_t>(planned.params.nTiles, static_cast<uint64_t>(c->smCount) * static_cast<uint64_t>(resident)));
+        }
+        if (std::getenv("FLATDD_B200_DEBUG") != nullptr) {
+            std::fprintf(stderr, "[flatdd_b200] block pass: %d block(s), tile 2^%d x %d buffer(s), %d warps%s, grid %d, smem %zu B, conflicts", count, planned.params.tileBits, planned.nBuffers, planned.warps, planned.ws ? " (warp-specialised)" : "", planned.grid, planned.smem);
+            for (int i = 0; i < count; ++i) std::fprintf(stderr, " %d(k%d,c%d)", planned.params.blocks[i].conflictWays, planned.params.blocks[i].k, planned.params.blocks[i].nCtx);
+            std::fprintf(stderr, "\n");
+        }
+        if (cachePlan) c->passPlans.emplace(key, planned);
+    }
+    planned.params.y = c->buf[c->cur];
+    planned.params.z = c->buf[c->cur ^ 1];
+    static const char* skipEnv = std::getenv("FLATDD_B200_BLOCK_SKIP");
+    planned.params.debugSkip = skipEnv != nullptr ? static_cast<uint32_t>(std::atoi(skipEnv)) : 0u;
+    static const bool clocksEnv = std::getenv("FLATDD_B200_BLOCK_CLOCKS") != nullptr;
+    static long long* dClocks = nullptr;
+    if (clocksEnv && dClocks == nullptr) CUDA_TRY(cudaMalloc(&dClocks, sizeof(long long) * 4 * 16 * 1024));
+    planned.params.debugClocks = clocksEnv ? dClocks : nullptr;
+    {
+        Timed t(c);
+        if (planned.ws) {
+            dmavm_block_ws_kernel<<<planned.grid, kBlockThreads, planned.smem, c->stream>>>(planned.params, planned.maxUnits, planned.nBuffers);
+        } else if (planned.warps == 16) {
+            dmavm_block_kernel<16, 1><<<planned.grid, 32 * 16, planned.smem, c->stream>>>(planned.params, planned.maxUnits, planned.nBuffers);
+        } else if (planned.unitsPerIter == 2) {
+            dmavm_block_kernel<8, 2><<<planned.grid, 32 * 8, planned.smem, c->stream>>>(planned.params, planned.maxUnits, planned.nBuffers);
+        } else {
+            dmavm_block_kernel<8, 1><<<planned.grid, 32 * 8, planned.smem, c->stream>>>(planned.params, planned.maxUnits, planned.nBuffers);
+        }
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (clocksEnv && planned.ws && count == 1) {
+        std::vector<long long> h(static_cast<size_t>(planned.grid) * kComputeWarps * 4);
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        CUDA_TRY(cudaMemcpy(h.data(), dClocks, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        double w = 0, r = 0, t = 0, tiles = 0;
+        for (size_t i = 0; i < h.size(); i += 4) {
+            w += static_cast<double>(h[i]);
+            r += static_cast<double>(h[i + 1]);
+            t += static_cast<double>(h[i + 2]);
+            tiles += static_cast<double>(h[i + 3]);
+        }
+        std::fprintf(stderr, "[flatdd_b200] clocks per warp and tile: wait %.0f, blocks %.0f, total %.0f (k=%d, units per warp and tile %.2f)\n", w / tiles, r / tiles,
+                     t / tiles, planned.params.blocks[0].k, static_cast<double>(planned.params.blocks[0].nUnits) / kComputeWarps);
+    }
+    static const bool passLog = std::getenv("FLATDD_B200_PASSLOG") != nullptr; // experiments: one line per pass with its device time
+    if (passLog && c->timing) {
+        std::fprintf(stderr, "[flatdd_b200] pass blocks=%d tile=2^%d buffers=%d k=", count, planned.params.tileBits, planned.nBuffers);
+        for (int i = 0; i < count; ++i) std::fprintf(stderr, "%d", planned.params.blocks[i].k);
+        std::fprintf(stderr, " ctx=");
+        for (int i = 0; i < count; ++i) std::fprintf(stderr, "%d,", planned.params.blocks[i].nCtx);
+        std::fprintf(stderr, " ms=%.4f\n", c->lastMs);
+    }
+    c->launches++;
+    c->blockLaunches++;
+    c->blocksApplied += static_cast<uint64_t>(count);
+    c->cur ^= 1;
+    return true;
+}
+
+void walkWithTables(fdd_ctx* c, const fdd_gate* gate) {
+    if (gate->dBlob == nullptr && gate->source != nullptr) {
+        auto* g = const_cast<fdd_gate*>(gate);
+        g->host = compileGate(*g->source, c->nLocal);
+        uploadGate(g, c->stream);
+    }
+    launchWalk(c, gate);
+}
+
+// gates[0..count) in order: consecutive blocks share a pass while they fit one tile, everything else takes the older kernels
+void applyGates(fdd_ctx* c, const fdd_gate* const* gates, int count, bool cachePlan) {
+    int i = 0;
+    while (i < count) {
+        if (!usesBlockPath(c, gates[i])) {
+            walkWithTables(c, gates[i]);
+            ++i;
+            continue;
+        }
+        std::vector<const DenseBlock*> group{gates[i]->block.get()};
+        int j = i + 1;
+        const int cap = std::max(1, std::min(c->blockMaxPerPass, kPassMaxBlocks));
+        while (j < count && j - i < cap && usesBlockPath(c, gates[j])) {
+            group.push_back(gates[j]->block.get());
+            const int need = minTileBits(group.data(), static_cast<int>(group.size()), c->nLocal);
+            if (need < 0 || need > std::min(c->nLocal, kPassMaxTileBits)) {
+                group.pop_back();
+                break;
+            }
+            ++j;
+        }
+        // a group whose fragment shapes cannot be planned shrinks from the back; a single block that cannot falls back
+        int n = j - i;
+        while (n >= 1 && !launchPass(c, gates + i, n, cachePlan)) --n;
+        if (n == 0) {
+            walkWithTables(c, gates[i]);
+            n = 1;
+        }
+        i += n;
+    }
 }
 
 fdd_ctx* createCtx(int nQubits, int device, int rank, int world) {
@@ -610,6 +841,13 @@ int fdd_set_option(fdd_ctx* ctx, const char* key, long value) {
         else if (k == "flat_table") ctx->flatTable = static_cast<int>(value);
         else if (k == "exchange_unroll") ctx->exchangeUnroll = static_cast<int>(value);
         else if (k == "exchange_ctas_per_sm") ctx->exchangeCtasPerSm = static_cast<int>(value);
+        else if (k == "block_kernel") ctx->blockKernel = static_cast<int>(value);
+        else if (k == "block_tile_bits") ctx->blockTileBits = static_cast<int>(value);
+        else if (k == "block_max_per_pass") ctx->blockMaxPerPass = static_cast<int>(value);
+        else if (k == "block_buffers") ctx->blockBuffers = static_cast<int>(value);
+        else if (k == "block_warps") ctx->blockWarps = static_cast<int>(value);
+        else if (k == "block_units") ctx->blockUnits = static_cast<int>(value);
+        else if (k == "block_ws") ctx->blockWs = static_cast<int>(value);
         else throw std::invalid_argument("unknown option " + k);
     });
 }
@@ -635,6 +873,15 @@ int fdd_get_option(const fdd_ctx* ctx, const char* key, long* value) {
         else if (k == "launches") *value = static_cast<long>(ctx->launches);
         else if (k == "tensor_core_launches") *value = static_cast<long>(ctx->tensorCoreLaunches);
         else if (k == "exchanges") *value = static_cast<long>(ctx->exchanges);
+        else if (k == "block_kernel") *value = ctx->blockKernel;
+        else if (k == "block_tile_bits") *value = ctx->blockTileBits;
+        else if (k == "block_max_per_pass") *value = ctx->blockMaxPerPass;
+        else if (k == "block_buffers") *value = ctx->blockBuffers;
+        else if (k == "block_warps") *value = ctx->blockWarps;
+        else if (k == "block_units") *value = ctx->blockUnits;
+        else if (k == "block_ws") *value = ctx->blockWs;
+        else if (k == "block_launches") *value = static_cast<long>(ctx->blockLaunches);
+        else if (k == "blocks_applied") *value = static_cast<long>(ctx->blocksApplied);
         else throw std::invalid_argument("unknown option " + k);
     });
 }
@@ -856,6 +1103,7 @@ int fdd_gate_compile(fdd_ctx* ctx, const fdd_matdd* gate, fdd_gate** out) {
             g->host = compileGate(*gate, ctx->nLocal);
             g->device = ctx->device;
             uploadGate(g, ctx->stream);
+            attachBlock(ctx, g, *gate);
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         } catch (...) {
             freeGate(g, nullptr);
@@ -869,7 +1117,7 @@ int fdd_gate_apply(fdd_ctx* ctx, const fdd_gate* gate) {
     return guarded([&] {
         if (ctx == nullptr || gate == nullptr) throw std::invalid_argument("null argument");
         useDevice(ctx);
-        launchWalk(ctx, gate);
+        applyGates(ctx, &gate, 1, true);
     });
 }
 
@@ -879,8 +1127,8 @@ int fdd_gate_apply_many(fdd_ctx* ctx, const fdd_gate* const* gates, int count) {
         useDevice(ctx);
         for (int i = 0; i < count; ++i) {
             if (gates[i] == nullptr) throw std::invalid_argument("null gate in the list");
-            launchWalk(ctx, gates[i]);
         }
+        applyGates(ctx, gates, count, true);
     });
 }
 
@@ -913,6 +1161,8 @@ static long gateFact(const CompiledGate& h, const std::string& k) {
 
 long fdd_gate_info(const fdd_gate* gate, const char* key) {
     if (gate == nullptr || key == nullptr) return -1;
+    if (std::string(key) == "block_targets") return gate->block ? gate->block->k() : -1;
+    if (std::string(key) == "block_context") return gate->block ? static_cast<long>(gate->block->ctx.size()) : -1;
     return gateFact(gate->host, key);
 }
 
@@ -923,22 +1173,36 @@ int fdd_matdd_info(const fdd_matdd* gate, const char* key, long* value) {
     });
 }
 
-int fdd_apply(fdd_ctx* ctx, const fdd_matdd* gate) {
+int fdd_apply_many(fdd_ctx* ctx, const fdd_matdd* gates, int count) {
     return guarded([&] {
-        if (ctx == nullptr || gate == nullptr) throw std::invalid_argument("null argument");
+        if (ctx == nullptr || (gates == nullptr && count > 0)) throw std::invalid_argument("null argument");
         useDevice(ctx);
-        auto g = new fdd_gate();
+        std::vector<fdd_gate*> owned;
+        auto release = [&] {
+            for (fdd_gate* g : owned) freeGate(g, ctx->stream); // stream ordered: released after the kernels have run
+        };
         try {
-            g->host = compileGate(*gate, ctx->nLocal);
-            g->device = ctx->device;
-            uploadGate(g, ctx->stream);
-            launchWalk(ctx, g);
+            for (int i = 0; i < count; ++i) {
+                const fdd_matdd& dd = gates[i];
+                if (dd.n_qubits != ctx->n) throw std::invalid_argument("gate has " + std::to_string(dd.n_qubits) + " qubits, context has " + std::to_string(ctx->n));
+                auto g = new fdd_gate();
+                owned.push_back(g);
+                g->device = ctx->device;
+                g->source = &dd; // the older kernels' tables are only made if a launch needs them
+                attachBlock(ctx, g, dd);
+            }
+            applyGates(ctx, owned.data(), count, false);
         } catch (...) {
-            freeGate(g, ctx->stream);
+            release();
             throw;
         }
-        freeGate(g, ctx->stream); // stream ordered: released after the kernel has run
+        release();
     });
+}
+
+int fdd_apply(fdd_ctx* ctx, const fdd_matdd* gate) {
+    if (gate == nullptr) return fail(FDD_ERR_INVALID, "null argument");
+    return fdd_apply_many(ctx, gate, 1);
 }
 
 int fdd_ddarr_multiply(const fdd_matdd* gate, const double* y_real, const double* y_imag, double* z_real, double* z_imag,

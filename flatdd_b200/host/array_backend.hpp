@@ -31,6 +31,11 @@ public:
     // one DMAVM (reference: DDArrMultiplyIP / DDArrMultiplyOP); `nOriginalGates` = how many
     // circuit operations were fused into this matrix (bookkeeping only)
     virtual void apply(const FlatMatDD& gate, int nOriginalGates) = 0;
+    // a stretch of the schedule in one boundary call (reference: the executor loop, src/SwitchSimulator.cpp:386-412); the GPU
+    // backend keeps the state tile-resident across consecutive dense blocks.  Default: one apply per gate.
+    virtual void applyMany(const std::vector<FlatMatDD>& gates, const std::vector<int>& nOriginalGates) {
+        for (std::size_t i = 0; i < gates.size(); ++i) apply(gates[i], nOriginalGates[i]);
+    }
     // copy the current state into SoA arrays of 2^n_local doubles (reference: getVector)
     virtual void getState(double* real, double* imag) = 0;
     virtual void synchronize() {}
@@ -78,6 +83,12 @@ public:
     void apply(const FlatMatDD& gate, int /*nOriginalGates*/) override {
         const fdd_matdd m = view(gate);
         fddCheck(fdd_apply(ctx_, &m), "fdd_apply");
+    }
+    void applyMany(const std::vector<FlatMatDD>& gates, const std::vector<int>& /*nOriginalGates*/) override {
+        std::vector<fdd_matdd> views;
+        views.reserve(gates.size());
+        for (const auto& g : gates) views.push_back(view(g));
+        fddCheck(fdd_apply_many(ctx_, views.data(), static_cast<int>(views.size())), "fdd_apply_many");
     }
     void getState(double* real, double* imag) override { fddCheck(fdd_get_state(ctx_, real, imag), "fdd_get_state"); }
     void synchronize() override { fddCheck(fdd_synchronize(ctx_), "fdd_synchronize"); }
@@ -175,6 +186,11 @@ public:
     void apply(const FlatMatDD& gate, int nOriginalGates) override {
         for (auto* s : sinks_) {
             s->apply(gate, nOriginalGates);
+        }
+    }
+    void applyMany(const std::vector<FlatMatDD>& gates, const std::vector<int>& nOriginalGates) override {
+        for (auto* s : sinks_) {
+            s->applyMany(gates, nOriginalGates);
         }
     }
     // the first sink owns the state

@@ -160,6 +160,7 @@ public:
     double arrayPhaseTime = 0.0;
     double kernelMsTotal = 0.0;    // sum of device times of the DMAVM launches (needs per-launch timing on the backend)
     bool verbose = true;
+    bool timePerGate = false;      // one boundary call per gate (per-launch device times) instead of one per stretch of the schedule
 
 private:
     using Clock = std::chrono::steady_clock;
@@ -657,16 +658,41 @@ private:
             std::cout << "Merged Gate Number: " << s.gates.size() << "\n";
         }
         const auto t0 = Clock::now();
-        for (std::size_t i = 0; i < s.gates.size(); ++i) {
+        // Stretches of the schedule between two layout steps cross the boundary in one call (ArrayBackend::applyMany), so the
+        // GPU library can keep the state tile-resident across consecutive dense blocks.  With per-launch timing on
+        // (--time-gates) every gate is its own call, as before.
+        std::vector<FlatMatDD> stretch;
+        std::vector<int> stretchOriginals;
+        auto flush = [&]() {
+            if (stretch.empty()) return;
             const auto tg = Clock::now();
-            for (const auto& st : s.layoutBefore[i]) runLayoutStep(st);
-            if (!isIdentity(s.gates[i])) {
-                launch(s.gates[i], s.originals[i]);
-            } else {
-                arrayPhaseOps += static_cast<std::size_t>(s.originals[i]);
+            backend->applyMany(stretch, stretchOriginals);
+            const double each = since(tg) / static_cast<double>(stretch.size());
+            for (std::size_t k = 0; k < stretch.size(); ++k) timeRecord2.push_back(each);
+            kernelMsTotal += backend->lastKernelMs();
+            launches += stretch.size();
+            stretch.clear();
+            stretchOriginals.clear();
+            hostValid = false;
+        };
+        for (std::size_t i = 0; i < s.gates.size(); ++i) {
+            if (!s.layoutBefore[i].empty()) {
+                flush();
+                for (const auto& st : s.layoutBefore[i]) runLayoutStep(st);
             }
-            timeRecord2.push_back(since(tg));
+            arrayPhaseOps += static_cast<std::size_t>(s.originals[i]);
+            if (isIdentity(s.gates[i])) continue;
+            if (timePerGate) {
+                const auto tg = Clock::now();
+                arrayPhaseOps -= static_cast<std::size_t>(s.originals[i]);
+                launch(s.gates[i], s.originals[i]);
+                timeRecord2.push_back(since(tg));
+            } else {
+                stretch.push_back(flatten<4, MEdge, WeightTraits>(s.gates[i], nq()));
+                stretchOriginals.push_back(s.originals[i]);
+            }
         }
+        flush();
         backend->synchronize();
         arrayPhaseTime = since(t0);
         if (verbose) {

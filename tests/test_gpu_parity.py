@@ -330,6 +330,7 @@ def test_tensor_core_path_vs_numpy_and_fma_path(n, targets, kind):
     out = {}
     for dmma in (1, 0):
         with Context(n) as ctx:
+            ctx.set_option("block_kernel", 0)  # this test is about the tile kernel's paths
             ctx.set_option("dmma", dmma)
             ctx.set_state(yr, yi)
             ctx.apply(gate)
@@ -339,6 +340,7 @@ def test_tensor_core_path_vs_numpy_and_fma_path(n, targets, kind):
             assert ctx.get_option("context_table_launches") == (2 if dmma else 0)
     if True:  # the walk inside the launch (no context table) gives the same state
         with Context(n) as ctx:
+            ctx.set_option("block_kernel", 0)  # this test is about the tile kernel's paths
             ctx.set_option("context_table", 0)
             ctx.set_state(yr, yi)
             ctx.apply(gate)
@@ -364,6 +366,7 @@ def test_tensor_core_path_full_size():
     targets = [25, 17, 11, 6]
     u = B.random_unitary(4, rng)
     with Context(n) as ctx:
+        ctx.set_option("block_kernel", 0)  # this test is about the tile kernel's tensor-core path
         ctx.set_state(yr, yi)
         ctx.apply(B.gate_dd(n, targets, u))
         assert abs(ctx.norm2() - 1.0) < 1e-12
@@ -399,6 +402,7 @@ def test_flat_table_path_vs_numpy_and_mode3(n, targets, flat):
     out = {}
     for on in (1, 0):
         with Context(n) as ctx:
+            ctx.set_option("block_kernel", 0)  # this test is about the tile kernel's paths
             ctx.set_option("flat_table", on)
             ctx.set_state(yr, yi)
             ctx.apply(gate)

@@ -28,8 +28,9 @@ def main():
             for i, (r, g) in enumerate(gates):
                 ctx.apply_compiled(g)
                 rows.append((i, r.n_original_gates, r.dd.n_nodes, g.info("max_paths"), g.info("max_sub_k"), g.info("upper_depth"),
-                             g.info("upper_nodes"), g.info("sub_tables"), g.info("top_level"), g.info("tileable"), g.info("non_diag_upper"), g.info("uniform"), ctx.last_kernel_ms()))
-    hdr = "idx,orig,nodes,paths,k,depth,upper,subs,top,tileable,ndu,uniform,ms"
+                             g.info("upper_nodes"), g.info("sub_tables"), g.info("top_level"), g.info("tileable"), g.info("non_diag_upper"), g.info("uniform"),
+                             g.info("block_targets"), g.info("block_context"), ctx.last_kernel_ms()))
+    hdr = "idx,orig,nodes,paths,k,depth,upper,subs,top,tileable,ndu,uniform,block_k,block_ctx,ms"
     lines = [hdr] + [",".join(str(x) for x in r) for r in rows]
     if out:
         Path(out).parent.mkdir(parents=True, exist_ok=True)
@@ -43,7 +44,9 @@ def main():
     for key in sorted(agg):
         v = agg[key]
         print(f"  paths={key[0]:3d} k={key[1]:2d}: {len(v):4d} launches, mean {sum(v) / len(v):.3f} ms, min {min(v):.3f}, max {max(v):.3f}")
-    uni = [r[-1] for r in rows if r[-2] == 1]
+    uni = [r[-1] for r in rows if r[11] == 1]
+    blk = [r[-1] for r in rows if r[12] >= 0]
+    print(f"  dense blocks: {len(blk)} of {len(rows)}" + (f", mean {sum(blk) / len(blk):.3f} ms" if blk else ""))
     print(f"  uniform gates: {len(uni)} of {len(rows)}" + (f", mean {sum(uni) / len(uni):.3f} ms" if uni else ""))
 
 
