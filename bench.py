@@ -298,6 +298,7 @@ def measure(workload: str, args, steps: int, warmup: int, with_e2e: bool) -> dic
     exchange_events = []
     launches0 = ctx.launch_count()
     tensor0 = ctx.get_option("tensor_core_launches")
+    passes0, blocks0 = ctx.get_option("block_launches"), ctx.get_option("blocks_applied")
     barrier()
     for s in range(steps):
         ev[3 * s].record(stream)
@@ -308,6 +309,16 @@ def measure(workload: str, args, steps: int, warmup: int, with_e2e: bool) -> dic
     barrier()
     launches = ctx.launch_count() - launches0
     tensor_launches = ctx.get_option("tensor_core_launches") - tensor0
+    block_passes = (ctx.get_option("block_launches") - passes0) // steps   # passes of the tile-resident dense-block kernel per step
+    blocks_applied = (ctx.get_option("blocks_applied") - blocks0) // steps  # fused gates those passes applied
+    # FP64 tensor-core work of a step: a 2^k x 2^k complex block is three real products of 2^k x 2^k x 2^n_local each
+    block_flops = 0.0
+    for st in sched:
+        if st[0] == "g":
+            for g in st[1]:
+                k = g.info("block_targets")
+                if k >= 3:
+                    block_flops += 3.0 * 2.0 * (1 << k) * local_dim
     total_ms = ev[0].elapsed_time(ev[3 * steps - 1])
     convert_ms = [ev[3 * s].elapsed_time(ev[3 * s + 1]) for s in range(steps)]
     body_ms = [ev[3 * s + 1].elapsed_time(ev[3 * s + 2]) for s in range(steps)]
@@ -389,19 +400,36 @@ def measure(workload: str, args, steps: int, warmup: int, with_e2e: bool) -> dic
         peaks = json.loads(peaks_file.read_text())
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    # DMAVM launch time: the step body minus the exchanges
-    launch_ms = (body_mean - exch_mean_ms * n_exch) / max(1, n_gates)
-    achieved = 32.0 * local_dim / (launch_ms * 1e-3) / 1e9
+    # DMAVM time: the step body minus the exchanges.  One LAUNCH of the dense-block kernel is one pass over the state that
+    # applies one or more fused gates to a tile held in shared memory; the algorithmic bytes of a launch are SURVEY.md 8(d)'s
+    # per-unit figure (32 * 2^n per applied fused gate) times the fused gates the launch applies.
+    dmavm_ms = body_mean - exch_mean_ms * n_exch
+    launch_ms = dmavm_ms / max(1, n_gates)  # per fused gate
+    other_launches = n_gates - blocks_applied  # fused gates that took one of the older kernels: one launch each
+    passes = block_passes + other_launches
+    achieved = 32.0 * local_dim * n_gates / (dmavm_ms * 1e-3) / 1e9
+    dram_gbs = 32.0 * local_dim * passes / (dmavm_ms * 1e-3) / 1e9
     traffic = None
-    tf = ROOT / "profiles" / "dmavm_traffic.json"
-    if tf.exists() and n_local == 26:
-        traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+    tf = ROOT / "profiles" / "r02_dmavm_traffic.json"
+    if tf.exists() and n_local == 26 and passes > 0:
+        table = json.loads(tf.read_text())
+        traffic = (table["dmavm_block_ws_kernel"]["dram_bytes_per_launch"] * block_passes +
+                   table["dmavm_tile_kernel"]["dram_bytes_per_launch"] * other_launches) / passes
+    tensor_peak = 44.2  # TFLOP/s, DMMA.8x8x4 alone on this pool's B200 (tools/dmma_probe.cu, profiles/r02_dmma_probe.jsonl)
     res = {
         "workload": workload, "n_qubits": n, "n_gates": n_gates, "n_exch": n_exch, "array_ops": array_ops, "n_local": n_local,
         "value": array_ops / (t_step_ms * 1e-3), "ms_per_step": t_step_ms, "convert_ms": statistics.mean(convert_ms),
-        "dmavm_ms_per_launch": launch_ms, "launches": int(launches), "tensor_core_launches": int(tensor_launches), "clocks": clocks,
+        "dmavm_ms_per_launch": dmavm_ms / max(1, passes), "dmavm_ms_per_fused_gate": launch_ms, "launches": int(launches), "passes": passes, "tensor_core_launches": int(tensor_launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "dmavm_tile_kernel", "peak_source": peak_src, "bytes_per_launch": 32 * local_dim,
+                     "kernel": "dmavm_block_ws_kernel" if block_passes >= other_launches else "dmavm_tile_kernel", "peak_source": peak_src,
+                     "launches_per_step": passes, "fused_gates_per_step": n_gates, "fused_gates_per_launch": n_gates / max(1, passes),
+                     "bytes_per_launch": 32 * local_dim * n_gates / max(1, passes),
+                     "definition": "algorithmic bytes = 32 * 2^n per applied fused gate (SURVEY.md 8d) x the fused gates a launch applies, / launch time; "
+                                   "a launch that keeps a tile resident for several fused gates moves 32 * 2^n bytes through HBM ONCE (see dram_*)",
+                     "dram_gbs": dram_gbs, "dram_frac": dram_gbs / peak, "dram_bytes_per_launch": 32 * local_dim,
+                     "tensor": {"pipe": "FP64 DMMA.8x8x4", "tflops": block_flops / (dmavm_ms * 1e-3) / 1e12, "peak_tflops": tensor_peak,
+                                "frac": block_flops / (dmavm_ms * 1e-3) / 1e12 / tensor_peak,
+                                "peak_source": "measured: DMMA alone, tools/dmma_probe.cu (44.2 TFLOP/s; 31-32 with the loop's shared-memory traffic and additions)"},
                      "convert_gbs": 16.0 * local_dim / (statistics.mean(convert_ms) * 1e-3) / 1e9},
         "check": {"norm2_device": norm2, "max_amp_err_vs_reference": amp_err, "reference_samples_checked": n_checked,
                   "reference": "unmodified reference FlatDD (oracle/ref_dump), sampled amplitudes in bench_inputs/samples/"
@@ -490,7 +518,7 @@ def gpu_arm(args) -> int:
             "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{workload} array phase: DD->array conversion + {main['n_gates']} fused DMAVM launches "
+            "config": {"workload": f"{workload} array phase: DD->array conversion + {main['n_gates']} fused gates in {main['passes']} DMAVM launches "
                                    f"({main['array_ops']} circuit ops after the switch)" + (f" + {n_exch} half-shard exchanges" if world > 1 else ""),
                        "n_qubits": main["n_qubits"], "state_bytes": 16 << main["n_qubits"],
                        "fusion": "per gate (fuse 0)" if "_f0" in workload else "dependency-graph fusion with the GPU cost model (fuse 4)",

@@ -28,7 +28,7 @@ EXPORTS = [
     "fdd_version", "fdd_last_error", "fdd_device_count", "fdd_create", "fdd_create_sharded", "fdd_destroy",
     "fdd_n_qubits", "fdd_n_local_qubits", "fdd_synchronize", "fdd_set_option", "fdd_get_option", "fdd_comm_unique_id", "fdd_comm_init",
     "fdd_exchange_qubits", "fdd_relabel_qubits", "fdd_barrier",
-    "fdd_convert", "fdd_apply", "fdd_apply_many", "fdd_gate_compile", "fdd_gate_apply", "fdd_gate_apply_many", "fdd_gate_free", "fdd_gate_info",
+    "fdd_convert", "fdd_apply", "fdd_apply_many", "fdd_block_from_matdd", "fdd_gate_compile", "fdd_gate_apply", "fdd_gate_apply_many", "fdd_gate_free", "fdd_gate_info",
     "fdd_ddarr_multiply", "fdd_mac_count", "fdd_cost_ip", "fdd_cost_op1", "fdd_cost_gpu", "fdd_matdd_info", "fdd_get_state",
     "fdd_set_state", "fdd_set_zero_state", "fdd_get_amplitudes", "fdd_get_amplitudes_at", "fdd_norm2", "fdd_sample", "fdd_state_device_ptr",
     "fdd_get_permutation", "fdd_canonicalize", "fdd_last_kernel_ms", "fdd_set_timing", "fdd_launch_count", "fdd_stream",

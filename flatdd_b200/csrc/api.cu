@@ -125,7 +125,9 @@ struct fdd_ctx {
     int exchangeCtasPerSm = 4;
     int blockKernel = 1;      // gates that are dense blocks (<= 4 non-diagonal qubits anywhere, <= 10 context qubits) take the tile-resident kernel
     int blockTileBits = 12;   // preferred tile size of a pass (log2 amplitudes); grows to 13 when the blocks of a pass need it
-    int blockMaxPerPass = kPassMaxBlocks; // 1: one pass per block (A/B against the fused passes)
+    int blockMaxPerPass = 4;  // blocks that may share a pass; 1: one pass per block (A/B against the fused passes)
+    int blockMaxTileBits = 12; // largest tile a pass of SEVERAL blocks may need (2^12: three tile buffers fit, copy and tensor work overlap;
+                               // 2^13 fills the shared memory with one buffer: measured slower than separate passes)
     int blockWarps = 0;       // experiments: 16 = sixteen warps per CTA with one unit per iteration
     int blockUnits = 2;       // units per iteration and warp (2: twelve independent tensor-core chains, one CTA per SM; 1: two CTAs per SM)
     int blockBuffers = 3;     // tile buffers per CTA when they fit (copy-in, tensor-core work and copy-out of consecutive tiles overlap)
@@ -694,7 +696,7 @@ void applyGates(fdd_ctx* c, const fdd_gate* const* gates, int count, bool cacheP
         while (j < count && j - i < cap && usesBlockPath(c, gates[j])) {
             group.push_back(gates[j]->block.get());
             const int need = minTileBits(group.data(), static_cast<int>(group.size()), c->nLocal);
-            if (need < 0 || need > std::min(c->nLocal, kPassMaxTileBits)) {
+            if (need < 0 || need > std::min(c->nLocal, std::min(kPassMaxTileBits, c->blockMaxTileBits))) {
                 group.pop_back();
                 break;
             }
@@ -848,6 +850,7 @@ int fdd_set_option(fdd_ctx* ctx, const char* key, long value) {
         else if (k == "block_warps") ctx->blockWarps = static_cast<int>(value);
         else if (k == "block_units") ctx->blockUnits = static_cast<int>(value);
         else if (k == "block_ws") ctx->blockWs = static_cast<int>(value);
+        else if (k == "block_max_tile_bits") ctx->blockMaxTileBits = static_cast<int>(value);
         else throw std::invalid_argument("unknown option " + k);
     });
 }
@@ -880,6 +883,7 @@ int fdd_get_option(const fdd_ctx* ctx, const char* key, long* value) {
         else if (k == "block_warps") *value = ctx->blockWarps;
         else if (k == "block_units") *value = ctx->blockUnits;
         else if (k == "block_ws") *value = ctx->blockWs;
+        else if (k == "block_max_tile_bits") *value = ctx->blockMaxTileBits;
         else if (k == "block_launches") *value = static_cast<long>(ctx->blockLaunches);
         else if (k == "blocks_applied") *value = static_cast<long>(ctx->blocksApplied);
         else throw std::invalid_argument("unknown option " + k);
@@ -1203,6 +1207,25 @@ int fdd_apply_many(fdd_ctx* ctx, const fdd_matdd* gates, int count) {
 int fdd_apply(fdd_ctx* ctx, const fdd_matdd* gate) {
     if (gate == nullptr) return fail(FDD_ERR_INVALID, "null argument");
     return fdd_apply_many(ctx, gate, 1);
+}
+
+int fdd_block_from_matdd(const fdd_matdd* gate, int max_controls, int32_t* n_targets, int32_t* targets, int32_t* n_controls,
+                         int32_t* controls, double* matrices, size_t capacity_doubles) {
+    return guarded([&] {
+        if (gate == nullptr || n_targets == nullptr || targets == nullptr || n_controls == nullptr || controls == nullptr) throw std::invalid_argument("null argument");
+        *n_targets = -1;
+        *n_controls = -1;
+        DenseBlock b;
+        if (!denseBlockFromDD(*gate, b, std::max(0, std::min(max_controls, kBlockMaxCtx)))) {
+            throw std::length_error("the gate is not a dense block (more than 4 non-diagonal qubits or too many context qubits)");
+        }
+        *n_targets = b.k();
+        *n_controls = static_cast<int32_t>(b.ctx.size());
+        for (int i = 0; i < b.k(); ++i) targets[i] = b.targets[static_cast<size_t>(i)];
+        for (size_t i = 0; i < b.ctx.size(); ++i) controls[i] = b.ctx[i];
+        if (matrices == nullptr || capacity_doubles < b.table.size()) throw std::invalid_argument("matrices buffer too small: 2 * 4^n_targets * 2^n_controls doubles are needed");
+        std::memcpy(matrices, b.table.data(), b.table.size() * sizeof(double));
+    });
 }
 
 int fdd_ddarr_multiply(const fdd_matdd* gate, const double* y_real, const double* y_imag, double* z_real, double* z_imag,

@@ -33,6 +33,7 @@
 #pragma once
 
 #include "array_backend.hpp"
+#include "block_fusion.hpp"
 #include "flatten.hpp"
 
 #include <algorithm>
@@ -43,6 +44,7 @@
 #include <cstdlib>
 #include <iostream>
 #include <memory>
+#include <sstream>
 #include <stdexcept>
 #include <unordered_map>
 #include <vector>
@@ -59,6 +61,14 @@ struct FusionPolicy {
     int maxTileQubits = 4;
     int maxLaneWithTile = -1;    // >= 0: a block with tile qubits may be non-diagonal on at most this many warp-lane qubits
     double budgetFactor = 2.2;   // accept a block while its modelled time <= budgetFactor x the HBM time of one pass
+    // fuse == 4 (dense-block fusion for the tile-resident kernel): a block has at most blockTargets non-diagonal qubits —
+    // anywhere, warp-lane qubits included — and at most blockContext qubits it depends on diagonally; the blocks of one
+    // pass over the state (consecutive blocks the library applies to a resident shared-memory tile) have at most passUpper
+    // target qubits above the five warp-lane qubits between them (a 2^12-amplitude tile) and number at most passBlocks
+    int blockTargets = 4;
+    int blockContext = 6;
+    int passUpper = 7;
+    int passBlocks = 1; // (1: blocks are formed without regard to their neighbours — measured best: fewest blocks; the library still shares passes where neighbours happen to fit)
 };
 
 template <class Package, class Qc, class DdOps, class WeightTraits> class GpuSwitchSimulator {
@@ -72,6 +82,10 @@ public:
         // experiments: FLATDD_B200_FUSE4="maxDenseQubits,maxTileQubits,budgetFactor[,maxLaneWithTile]" overrides the fuse == 4 policy
         if (const char* e = std::getenv("FLATDD_B200_FUSE4")) {
             std::sscanf(e, "%d,%d,%lf,%d", &policy.maxDenseQubits, &policy.maxTileQubits, &policy.budgetFactor, &policy.maxLaneWithTile);
+        }
+        // experiments: FLATDD_B200_BLOCKS="blockTargets,blockContext,passUpper,passBlocks" overrides the dense-block policy
+        if (const char* e = std::getenv("FLATDD_B200_BLOCKS")) {
+            std::sscanf(e, "%d,%d,%d,%d", &policy.blockTargets, &policy.blockContext, &policy.passUpper, &policy.passBlocks);
         }
     }
 
@@ -402,6 +416,18 @@ private:
             for (const auto& ex : plan) pending.push_back({true, ex.first, ex.second});
         }
         std::vector<LayoutStep> pending;
+        // dense-block fusion emits flat tables directly (no DD of the host package is built for a fused gate)
+        std::vector<FlatMatDD> flats;
+        std::vector<bool> flatIsIdentity;
+        void pushFlat(FlatMatDD&& flat, int count, bool identity) {
+            flats.push_back(std::move(flat));
+            flatIsIdentity.push_back(identity);
+            originals.push_back(count);
+            useCache.push_back(false);
+            layoutBefore.emplace_back(std::move(pending));
+            pending.clear();
+        }
+        [[nodiscard]] std::size_t size() const { return flats.empty() ? gates.size() : flats.size(); }
     };
 
     // cost of one gate under the active policy
@@ -450,7 +476,8 @@ private:
     // Greedy schedule over ops[first..] up to the first non-unitary operation.
     // Control flow of src/SwitchSimulator.cpp:271-340 (fuse 1), :341-372 (fuse 2); fuse 3 swaps the cost.
     Schedule buildSchedule(std::size_t first) {
-        if (fuse == 4) return buildScheduleDag(first);
+        if (fuse == 4) return buildScheduleBlocks(first);
+        if (fuse == 5) return buildScheduleDag(first);
         Schedule s;
         const auto& ops = qc->ops;
         auto current = dd->makeIdent(qc->getNqubits());
@@ -653,9 +680,223 @@ private:
         return s;
     }
 
+    // ---- dense-block fusion (fuse == 4) ---------------------------------------------------------------------------
+    // One circuit operation as a dense block on its own (physical) qubits.  The matrix comes from the DD the host package
+    // builds for the operation (so gate semantics, phases and control conventions are the reference's), extracted once per
+    // distinct (gate type, parameters, control/target order) and re-used for every placement of that gate.
+    struct OpBlock {
+        bool isBlock = false;
+        SmallGate gate;
+    };
+    OpBlock opBlockFor(const typename Qc::iterator::value_type::element_type* op, std::vector<LayoutStep>* deferred) {
+        OpBlock out;
+        if (worldSize > 1 && DdOps::isRelabelSwap(*op)) {
+            (void)gateFor(op, deferred); // absorbed into the layout
+            out.isBlock = true;
+            out.gate.table.assign(1, cplx(1.0, 0.0));
+            return out;
+        }
+        const std::string sig = DdOps::signature(*op);
+        std::vector<int> phys;
+        for (int q : DdOps::orderedQubits(*op)) phys.push_back(worldSize > 1 ? static_cast<int>(perm[static_cast<typename Perm::key_type>(q)]) : q);
+        std::string key;
+        std::vector<int> sorted = phys;
+        std::sort(sorted.begin(), sorted.end());
+        if (!sig.empty()) {
+            key = sig;
+            for (int q : phys) key += "," + std::to_string(std::lower_bound(sorted.begin(), sorted.end(), q) - sorted.begin());
+            const auto hit = opBlockCache.find(key);
+            if (hit != opBlockCache.end()) {
+                out = hit->second; // qubits are ranks among the operation's own qubits: place them
+                for (int& q : out.gate.targets) q = sorted[static_cast<std::size_t>(q)];
+                for (int& q : out.gate.ctx) q = sorted[static_cast<std::size_t>(q)];
+                return out;
+            }
+        }
+        const MEdge dd_ = worldSize > 1 ? DdOps::getDD(op, dd, perm) : DdOps::getDD(op, dd);
+        const auto flat = flatten<4, MEdge, WeightTraits>(dd_, nq());
+        out.isBlock = smallGateFromDD(flat, out.gate, policy.blockContext);
+        if (!sig.empty() && out.isBlock) {
+            OpBlock ranked = out;
+            bool placeable = true;
+            auto rankOf = [&](int q) {
+                const auto it = std::lower_bound(sorted.begin(), sorted.end(), q);
+                if (it == sorted.end() || *it != q) placeable = false;
+                return static_cast<int>(it - sorted.begin());
+            };
+            for (int& q : ranked.gate.targets) q = rankOf(q);
+            for (int& q : ranked.gate.ctx) q = rankOf(q);
+            if (placeable) opBlockCache.emplace(key, std::move(ranked));
+        }
+        return out;
+    }
+
+    Schedule buildScheduleBlocks(std::size_t first) {
+        Schedule s;
+        const auto& ops = qc->ops;
+        std::size_t last = first;
+        while (last < ops.size() && !ops[last]->isNonUnitaryOperation()) ++last;
+        const std::size_t count = last - first;
+        if (verbose) std::cout << "Using dense-block merge for the tile-resident GPU kernel... " << std::endl;
+        std::vector<std::vector<std::size_t>> succ(count);
+        std::vector<int> indeg(count, 0);
+        {
+            std::vector<long> lastOn(static_cast<std::size_t>(nq()), -1);
+            for (std::size_t i = 0; i < count; ++i) {
+                std::vector<long> preds;
+                for (int q : DdOps::allQubits(*ops[first + i])) {
+                    const long pOp = lastOn[static_cast<std::size_t>(q)];
+                    if (pOp >= 0 && std::find(preds.begin(), preds.end(), pOp) == preds.end()) preds.push_back(pOp);
+                    lastOn[static_cast<std::size_t>(q)] = static_cast<long>(i);
+                }
+                for (long pOp : preds) {
+                    succ[static_cast<std::size_t>(pOp)].push_back(i);
+                    ++indeg[i];
+                }
+            }
+        }
+        std::vector<std::size_t> ready; // kept sorted (program order)
+        for (std::size_t i = 0; i < count; ++i) {
+            if (indeg[i] == 0) ready.push_back(i);
+        }
+        const int local = worldSize > 1 ? nLocal() : nq();
+        const int laneBits = std::min(5, local);
+        auto physical = [&](int logical) {
+            return worldSize > 1 ? static_cast<int>(perm[static_cast<typename Perm::key_type>(logical)]) : logical;
+        };
+        auto needsGlobal = [&](std::size_t i) {
+            if (worldSize <= 1 || DdOps::isRelabelSwap(*ops[first + i])) return false;
+            for (int q : DdOps::nonDiagonalQubits(*ops[first + i])) {
+                if (physical(q) >= local) return true;
+            }
+            return false;
+        };
+        auto upperOf = [&](const std::vector<int>& qubits, std::vector<int> into) {
+            for (int q : qubits) {
+                if (q >= laneBits && std::find(into.begin(), into.end(), q) == into.end()) into.push_back(q);
+            }
+            return into;
+        };
+        BlockDDBuilder builder(nq());
+        std::vector<int> passUpperSet;
+        int passBlocks = 0;
+        std::size_t done = 0;
+        // blocks of operations, memoised per operation while the layout does not change
+        std::vector<OpBlock> memo(count);
+        std::vector<uint8_t> haveMemo(count, 0);
+        while (done < count) {
+            if (worldSize > 1) {
+                bool any = false;
+                for (std::size_t i : ready) any = any || !needsGlobal(i);
+                if (!any) {
+                    s.queueExchanges(planExchanges(first + ready.front()));
+                    std::fill(haveMemo.begin(), haveMemo.end(), 0); // the physical positions changed
+                    passUpperSet.clear();
+                    passBlocks = 0;
+                }
+            }
+            BlockAcc block;
+            int blockOps = 0;
+            bool progress = true;
+            bool emittedRaw = false;
+            while (progress && !emittedRaw) {
+                progress = false;
+                // operations that fit the block as it is (no new target qubit) go first, in program order; only when there is
+                // none does the block grow, by the admissible operation that adds the fewest target qubits (earliest on ties)
+                long pick = -1;
+                std::size_t pickGrowth = 99;
+                for (std::size_t r = 0; r < ready.size(); ++r) {
+                    const std::size_t i = ready[r];
+                    const auto* op = ops[first + i].get();
+                    if (needsGlobal(i)) continue;
+                    const bool relabelOnly = worldSize > 1 && DdOps::isRelabelSwap(*op);
+                    if (relabelOnly) { // free: absorbed into the layout right away
+                        pick = static_cast<long>(r);
+                        pickGrowth = 0;
+                        break;
+                    }
+                    if (!haveMemo[i]) {
+                        memo[i] = opBlockFor(op, &s.pending);
+                        haveMemo[i] = 1;
+                    }
+                    const OpBlock& ob = memo[i];
+                    if (ob.isBlock && ob.gate.isIdentity()) { // barriers, identities: free
+                        pick = static_cast<long>(r);
+                        pickGrowth = 0;
+                        break;
+                    }
+                    if (!ob.isBlock) {
+                        if (blockOps == 0 && pick < 0) { // wider than a block: goes through on its own once nothing is open
+                            pick = static_cast<long>(r);
+                            pickGrowth = 98;
+                        }
+                        continue;
+                    }
+                    std::vector<int> t2, c2;
+                    block.merged(ob.gate, t2, c2);
+                    if (static_cast<int>(t2.size()) > policy.blockTargets || static_cast<int>(c2.size()) > policy.blockContext) continue;
+                    if (static_cast<int>(upperOf(t2, passUpperSet).size()) > policy.passUpper) continue;
+                    const std::size_t growth = t2.size() - block.targets.size();
+                    if (growth < pickGrowth) {
+                        pick = static_cast<long>(r);
+                        pickGrowth = growth;
+                        if (growth == 0) break;
+                    }
+                }
+                if (pick < 0) break;
+                {
+                    const std::size_t r = static_cast<std::size_t>(pick);
+                    const std::size_t i = ready[r];
+                    const auto* op = ops[first + i].get();
+                    const bool relabelOnly = worldSize > 1 && DdOps::isRelabelSwap(*op);
+                    if (relabelOnly) {
+                        (void)opBlockFor(op, &s.pending);
+                        std::fill(haveMemo.begin(), haveMemo.end(), 0); // two logical qubits traded places
+                    } else if (!memo[i].isBlock) {
+                        // more than four non-diagonal qubits: as the DD the host package built, in a launch of its own
+                        const MEdge raw = worldSize > 1 ? DdOps::getDD(op, dd, perm) : DdOps::getDD(op, dd);
+                        s.pushFlat(flatten<4, MEdge, WeightTraits>(raw, nq()), 1, false);
+                        emittedRaw = true;
+                        passUpperSet.clear();
+                        passBlocks = 0;
+                    } else if (!memo[i].gate.isIdentity()) {
+                        block.apply(memo[i].gate);
+                    }
+                    if (!emittedRaw) ++blockOps;
+                    ready.erase(ready.begin() + static_cast<long>(r));
+                    for (std::size_t nxt : succ[i]) {
+                        if (--indeg[nxt] == 0) ready.insert(std::lower_bound(ready.begin(), ready.end(), nxt), nxt);
+                    }
+                    ++done;
+                    progress = true;
+                }
+            }
+            if (emittedRaw) continue;
+            if (blockOps == 0) {
+                if (passBlocks > 0) { // nothing fits next to the blocks of the current pass: open a new pass
+                    passUpperSet.clear();
+                    passBlocks = 0;
+                    continue;
+                }
+                throw std::runtime_error("dense-block fusion made no progress");
+            }
+            const bool identity = block.targets.empty() && block.ctx.empty() && block.table[0] == cplx(1.0, 0.0);
+            s.pushFlat(builder.build(block.targets, block.ctx, block.table), blockOps, identity);
+            if (!identity) {
+                passUpperSet = upperOf(block.targets, passUpperSet);
+                if (++passBlocks >= policy.passBlocks) {
+                    passUpperSet.clear();
+                    passBlocks = 0;
+                }
+            }
+        }
+        return s;
+    }
+    std::unordered_map<std::string, OpBlock> opBlockCache;
+
     void execute(const Schedule& s) {
         if (verbose) {
-            std::cout << "Merged Gate Number: " << s.gates.size() << "\n";
+            std::cout << "Merged Gate Number: " << s.size() << "\n";
         }
         const auto t0 = Clock::now();
         // Stretches of the schedule between two layout steps cross the boundary in one call (ArrayBackend::applyMany), so the
@@ -675,20 +916,28 @@ private:
             stretchOriginals.clear();
             hostValid = false;
         };
-        for (std::size_t i = 0; i < s.gates.size(); ++i) {
+        const bool flatSchedule = !s.flats.empty();
+        for (std::size_t i = 0; i < s.size(); ++i) {
             if (!s.layoutBefore[i].empty()) {
                 flush();
                 for (const auto& st : s.layoutBefore[i]) runLayoutStep(st);
             }
             arrayPhaseOps += static_cast<std::size_t>(s.originals[i]);
-            if (isIdentity(s.gates[i])) continue;
+            if (flatSchedule ? static_cast<bool>(s.flatIsIdentity[i]) : isIdentity(s.gates[i])) continue;
             if (timePerGate) {
                 const auto tg = Clock::now();
-                arrayPhaseOps -= static_cast<std::size_t>(s.originals[i]);
-                launch(s.gates[i], s.originals[i]);
+                if (flatSchedule) {
+                    backend->apply(s.flats[i], s.originals[i]);
+                    kernelMsTotal += backend->lastKernelMs();
+                    ++launches;
+                    hostValid = false;
+                } else {
+                    arrayPhaseOps -= static_cast<std::size_t>(s.originals[i]);
+                    launch(s.gates[i], s.originals[i]);
+                }
                 timeRecord2.push_back(since(tg));
             } else {
-                stretch.push_back(flatten<4, MEdge, WeightTraits>(s.gates[i], nq()));
+                stretch.push_back(flatSchedule ? s.flats[i] : flatten<4, MEdge, WeightTraits>(s.gates[i], nq()));
                 stretchOriginals.push_back(s.originals[i]);
             }
         }

@@ -11,6 +11,8 @@
 #include "dd/SwitchPackage.hpp"
 #include "gpu_switch_simulator.hpp"
 
+#include <sstream>
+
 namespace fddb200 {
 
 // Edge weights of the reference package are pairs of tagged pointers into the real-number
@@ -108,6 +110,23 @@ struct RefDdOps {
             changed = true; // k stays: a nested compound operation is expanded on the next pass
         }
         return changed;
+    }
+    // everything that defines the operation's matrix except WHICH qubits it sits on (empty: do not cache — compound operations)
+    static std::string signature(const qc::Operation& op) {
+        if (dynamic_cast<const qc::CompoundOperation*>(&op) != nullptr || op.isNonUnitaryOperation()) return {};
+        std::ostringstream out;
+        out << static_cast<int>(op.getType()) << '|' << op.getTargets().size() << '|';
+        for (const auto& c : op.getControls()) out << (c.type == qc::Control::Type::Pos ? 'p' : 'n');
+        out << '|' << std::hexfloat;
+        for (const auto p : op.getParameter()) out << p << ';';
+        return out.str();
+    }
+    // controls (ascending, as the IR keeps them) followed by the targets in the operation's own order
+    static std::vector<int> orderedQubits(const qc::Operation& op) {
+        std::vector<int> out;
+        for (const auto& c : op.getControls()) out.push_back(static_cast<int>(c.qubit));
+        for (const auto t : op.getTargets()) out.push_back(static_cast<int>(t));
+        return out;
     }
     static bool isMeasure(const qc::Operation& op) { return op.getType() == qc::Measure; }
     static bool isBarrier(const qc::Operation& op) { return op.getType() == qc::Barrier; }

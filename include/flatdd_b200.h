@@ -147,6 +147,16 @@ int fdd_apply(fdd_ctx* ctx, const fdd_matdd* gate);
  * the state while their target qubits fit one shared-memory tile — 32 bytes of HBM traffic per amplitude for the group
  * instead of per gate. */
 int fdd_apply_many(fdd_ctx* ctx, const fdd_matdd* gates, int count);
+/* Host only, no device needed: the gate as a DENSE BLOCK (north_star: "gate DDs are flattened to dense 2^k x 2^k blocks for
+ * the fused qubit set") — `targets`: its non-diagonal qubits (ascending, at most 4), `controls`: the other qubits its matrix
+ * depends on (diagonally: controls, phases; ascending, at most max_controls <= 10), `matrices`: [2^n_controls][2^k][2^k]
+ * complex (re, im) entries, row-major, index bit i <-> targets[i] / controls[i]; every entry is the product of the edge weights
+ * along its DD path, root first (the reference's order, include/dd/SwitchPackage.hpp:2221-2236).
+ * FDD_ERR_TOO_DENSE: the gate is not such a block.  FDD_ERR_INVALID with n_targets / n_controls filled in: the buffer is too
+ * small (2 * 4^k * 2^c doubles are needed).  The fusion pass of the host driver (flatdd_b200/host/block_fusion.hpp) uses this
+ * once per distinct circuit operation. */
+int fdd_block_from_matdd(const fdd_matdd* gate, int max_controls, int32_t* n_targets, int32_t* targets, int32_t* n_controls,
+                         int32_t* controls, double* matrices, size_t capacity_doubles);
 /* Same in two steps, so a schedule can be compiled once and replayed. */
 int fdd_gate_compile(fdd_ctx* ctx, const fdd_matdd* gate, fdd_gate** out);
 int fdd_gate_apply(fdd_ctx* ctx, const fdd_gate* gate);

@@ -62,10 +62,10 @@ def test_controlled_block_vs_oracle_and_old_kernels(layout, tile_bits):
 
 @pytest.mark.parametrize("sets,passes", [
     (([5, 6, 7, 8], [9, 10, 11, 2]), 1),                 # 7 upper targets: one 12-bit tile
-    (([5, 6, 7, 8], [9, 10, 11, 12]), 1),                # 8 upper targets: one 13-bit tile
-    (([5, 6, 7, 8], [9, 10, 11, 12], [13, 0, 1]), 2),    # the third block does not fit the tile of the first two
+    (([5, 6, 7, 8], [9, 10, 11, 12]), 2),                # 8 upper targets would need a 13-bit tile (one buffer): two passes by default
+    (([5, 6, 7, 8], [9, 10, 11, 2], [13, 0, 1]), 2),     # the third block does not fit the tile of the first two
     (([0, 1, 6, 7], [6, 7, 8, 9], [2, 3, 10]), 1),
-    (([13], [3, 4], [5, 6, 7], [8, 9, 10, 11]), 1),
+    (([13], [3, 4], [5, 6], [8, 9, 10, 11]), 1),         # seven upper targets between four blocks (the small ones are padded with lane qubits)
 ])
 def test_blocks_share_a_pass(sets, passes):
     n = 15
@@ -113,12 +113,27 @@ def test_reference_schedules_on_the_block_path(case):
     assert G.max_amp_err(out[1][0], out[1][1], out[0][0], out[0][1]) < 1e-13
 
 
+def test_thirteen_bit_tile_when_asked_for():
+    """block_max_tile_bits = 13: eight upper targets share one pass (single tile buffer)."""
+    n = 15
+    rng = np.random.default_rng(13)
+    sets = ([5, 6, 7, 8], [9, 10, 11, 12])
+    gates = [B.gate_dd(n, s, B.random_unitary(len(s), rng)) for s in sets]
+    yr, yi = B.random_state(n, rng)
+    re, im, stats = apply_all(n, gates, yr, yi, [("block_max_tile_bits", 13)], many=True)
+    assert stats["block_launches"] == 1 and stats["blocks_applied"] == 2
+    wr, wi = yr, yi
+    for g in gates:
+        wr, wi = pyoracle.dmavm(g, wr, wi)
+    assert G.max_amp_err(re, im, wr, wi) < AMP_TOL
+
+
 def test_full_size_pair_round_trip():
-    """n = 26: two dense 4-qubit blocks on disjoint upper qubits in one pass (a 13-bit tile), undone by their adjoints."""
+    """n = 26: two dense 4-qubit blocks with seven upper qubits between them in one pass, undone by their adjoints."""
     n = 26
     rng = np.random.default_rng(2627)
     yr, yi = B.random_state(n, rng)
-    ta, tb = [25, 17, 11, 6], [22, 9, 14, 19]
+    ta, tb = [25, 17, 11, 6], [22, 9, 14, 3]
     ua, ub = B.random_unitary(4, rng), B.random_unitary(4, rng)
     with Context(n) as ctx:
         ctx.set_state(yr, yi)
