@@ -81,6 +81,7 @@ int main(int argc, char** argv) {
     std::unique_ptr<fddb200::GpuArrayBackend> gpu;
     std::unique_ptr<fddb200::TraceRecorder> recorder;
     std::unique_ptr<fddb200::TeeBackend> tee;
+    std::unique_ptr<fddb200::BatchingBackend> batching;
     try {
         sa::Circuit circuit = sa::parseQasmFile(args.str("file"));
         const int nQubits = circuit.nQubits;
@@ -105,6 +106,11 @@ int main(int argc, char** argv) {
             if (recorder) {
                 tee = std::make_unique<fddb200::TeeBackend>(std::vector<fddb200::ArrayBackend*>{gpu.get(), recorder.get()});
                 backend = tee.get();
+            }
+            if (!args.has("time-gates")) {
+                // consecutive launches cross the boundary together: the library keeps the state tile-resident across dense blocks
+                batching = std::make_unique<fddb200::BatchingBackend>(backend);
+                backend = batching.get();
             }
         }
         if (world > 1) recorder->setWorldSize(world);

@@ -156,6 +156,11 @@ struct fdd_ctx {
     ncclComm_t comm = nullptr;
     double* dBarrier = nullptr;
     uint64_t exchanges = 0;
+    // exchange ordering without NCCL calls: two epoch words per rank in peer-mapped memory (comm.cuh)
+    uint32_t* dFlags = nullptr;                       // [0] ready epoch, [1] done epoch, [2] CTA counter (local use)
+    const uint32_t* peerFlags[kMaxPeers] = {};
+    uint32_t exchangeEpoch = 0;
+    int exchangeFlags = 1;    // 1: flag protocol inside the exchange kernel; 0: two stream-ordered NCCL barriers around it
 
     [[nodiscard]] uint64_t localDim() const { return uint64_t{1} << nLocal; }
 };
@@ -804,6 +809,10 @@ int fdd_destroy(fdd_ctx* ctx) {
         } catch (...) {
         }
     }
+    for (int r = 0; r < kMaxPeers; ++r) {
+        if (ctx->peerFlags[r] != nullptr && r != ctx->rank) cudaIpcCloseMemHandle(const_cast<uint32_t*>(ctx->peerFlags[r]));
+    }
+    cudaFree(ctx->dFlags);
     cudaFree(ctx->dBarrier);
     cudaFree(ctx->buf[0]);
     cudaFree(ctx->buf[1]);
@@ -851,6 +860,7 @@ int fdd_set_option(fdd_ctx* ctx, const char* key, long value) {
         else if (k == "block_units") ctx->blockUnits = static_cast<int>(value);
         else if (k == "block_ws") ctx->blockWs = static_cast<int>(value);
         else if (k == "block_max_tile_bits") ctx->blockMaxTileBits = static_cast<int>(value);
+        else if (k == "exchange_flags") ctx->exchangeFlags = static_cast<int>(value);
         else throw std::invalid_argument("unknown option " + k);
     });
 }
@@ -884,6 +894,7 @@ int fdd_get_option(const fdd_ctx* ctx, const char* key, long* value) {
         else if (k == "block_units") *value = ctx->blockUnits;
         else if (k == "block_ws") *value = ctx->blockWs;
         else if (k == "block_max_tile_bits") *value = ctx->blockMaxTileBits;
+        else if (k == "exchange_flags") *value = ctx->exchangeFlags;
         else if (k == "block_launches") *value = static_cast<long>(ctx->blockLaunches);
         else if (k == "blocks_applied") *value = static_cast<long>(ctx->blocksApplied);
         else throw std::invalid_argument("unknown option " + k);
@@ -916,12 +927,15 @@ int fdd_comm_init(fdd_ctx* ctx, const void* id128) {
         NCCL_TRY(nccl.CommInitRank(&ctx->comm, ctx->world, id, ctx->rank));
         CUDA_TRY(cudaMalloc(&ctx->dBarrier, sizeof(double)));
         CUDA_TRY(cudaMemsetAsync(ctx->dBarrier, 0, sizeof(double), ctx->stream));
-        // trade CUDA IPC handles of both state buffers
+        // trade CUDA IPC handles of both state buffers and of the flag words
+        CUDA_TRY(cudaMalloc(&ctx->dFlags, 256));
+        CUDA_TRY(cudaMemsetAsync(ctx->dFlags, 0, 256, ctx->stream));
         constexpr size_t kH = sizeof(cudaIpcMemHandle_t);
-        std::vector<unsigned char> mineH(2 * kH), all(2 * kH * static_cast<size_t>(ctx->world));
-        for (int b = 0; b < 2; ++b) {
+        constexpr int kHandles = 3;
+        std::vector<unsigned char> mineH(kHandles * kH), all(kHandles * kH * static_cast<size_t>(ctx->world));
+        for (int b = 0; b < kHandles; ++b) {
             cudaIpcMemHandle_t h;
-            CUDA_TRY(cudaIpcGetMemHandle(&h, ctx->buf[b]));
+            CUDA_TRY(cudaIpcGetMemHandle(&h, b < 2 ? static_cast<void*>(ctx->buf[b]) : static_cast<void*>(ctx->dFlags)));
             std::memcpy(mineH.data() + b * kH, &h, kH);
         }
         unsigned char* dH = nullptr;
@@ -932,18 +946,23 @@ int fdd_comm_init(fdd_ctx* ctx, const void* id128) {
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         CUDA_TRY(cudaFree(dH));
         for (int r = 0; r < ctx->world; ++r) {
-            for (int b = 0; b < 2; ++b) {
+            for (int b = 0; b < kHandles; ++b) {
                 if (r == ctx->rank) {
-                    ctx->peerBuf[b][r] = ctx->buf[b];
+                    if (b < 2) ctx->peerBuf[b][r] = ctx->buf[b];
+                    else ctx->peerFlags[r] = ctx->dFlags;
                     continue;
                 }
                 cudaIpcMemHandle_t h;
-                std::memcpy(&h, all.data() + (static_cast<size_t>(r) * 2 + b) * kH, kH);
+                std::memcpy(&h, all.data() + (static_cast<size_t>(r) * kHandles + b) * kH, kH);
                 void* p = nullptr;
                 CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-                ctx->peerBuf[b][r] = static_cast<const double2*>(p);
+                if (b < 2) ctx->peerBuf[b][r] = static_cast<const double2*>(p);
+                else ctx->peerFlags[r] = static_cast<const uint32_t*>(p);
             }
         }
+        // nobody may poll a flag word before its owner has zeroed it
+        NCCL_TRY(nccl.AllReduce(ctx->dBarrier, ctx->dBarrier, 1, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     });
 }
 
@@ -970,7 +989,22 @@ void exchangeBits(fdd_ctx* c, int pg, int pl, int method) {
     const int partner = c->rank ^ (1 << gbit);
     const int myBit = (c->rank >> gbit) & 1;
     const uint64_t dim = c->localDim();
-    if (method == 0) {
+    if (method == 0 && c->exchangeFlags) {
+        // ordering inside the kernel: flag words in peer memory (comm.cuh), no NCCL call
+        const uint32_t epoch = ++c->exchangeEpoch;
+        const int grid = c->smCount * (c->exchangeCtasPerSm > 0 ? c->exchangeCtasPerSm : 4);
+        unsigned int* counter = reinterpret_cast<unsigned int*>(c->dFlags + 2);
+        auto launch = [&](auto kernel) {
+            kernel<<<grid, 256, 0, c->stream>>>(c->buf[c->cur], c->peerBuf[c->cur][partner], c->buf[c->cur ^ 1], dim, pl, myBit, c->dFlags,
+                                                c->peerFlags[partner], epoch, counter);
+        };
+        if (c->exchangeUnroll == 4) launch(exchange_p2p_flag_kernel<4>);
+        else if (c->exchangeUnroll == 16) launch(exchange_p2p_flag_kernel<16>);
+        else launch(exchange_p2p_flag_kernel<8>);
+        CUDA_TRY(cudaGetLastError());
+        c->launches++;
+        c->cur ^= 1;
+    } else if (method == 0) {
         streamBarrier(c); // every rank has finished writing its current buffer
         const int grid = c->smCount * (c->exchangeCtasPerSm > 0 ? c->exchangeCtasPerSm : 4);
         if (c->exchangeUnroll == 4) {

@@ -217,111 +217,143 @@ bool planPass(const DenseBlock* const* blocks, int count, int nLocal, int rank, 
     pass.tileMask = tileMask;
     pass.nTiles = 1u << (nLocal - tileBits);
     pass.rankSegBits = static_cast<uint32_t>(rank) << (nLocal - kLaneBits);
+    // Warp-local passes: three tile bits outside every block's targets become the top unit bits of every block (see
+    // PassParams::warpLocal).  Tried first; when some block then lacks free bits for its fragment columns, plan without.
+    uint32_t allTargets = 0;
     for (int i = 0; i < count; ++i) {
-        const DenseBlock& blk = *blocks[i];
-        BlockDesc& d = pass.blocks[i];
-        const int k = blk.k();
-        if (k != 3 && k != 4) return false;
-        if (static_cast<int>(blk.ctx.size()) > kBlockMaxCtx) return false;
-        d.k = k;
-        d.nCtx = static_cast<uint8_t>(blk.ctx.size());
-        uint32_t used = 0; // tile bits that cannot be fragment columns: targets and in-tile context bits
-        std::array<int, 4> tp{};
-        for (int t = 0; t < k; ++t) {
-            tp[static_cast<std::size_t>(t)] = tilePos(blk.targets[static_cast<std::size_t>(t)]);
-            if (tp[static_cast<std::size_t>(t)] < 0) return false;
-            used |= 1u << tp[static_cast<std::size_t>(t)];
-        }
-        uint32_t ctxInTile = 0;
-        for (std::size_t j = 0; j < blk.ctx.size(); ++j) {
-            const int q = blk.ctx[j];
+        for (int q : blocks[i]->targets) {
             const int pos = tilePos(q);
-            if (pos >= 0) {
-                d.ctxSrc[j] = static_cast<uint8_t>(pos);
-                ctxInTile |= 1u << pos;
-            } else {
-                d.ctxSrc[j] = static_cast<uint8_t>(32 + (q - kLaneBits));
-            }
+            if (pos < 0) return false;
+            allTargets |= 1u << pos;
         }
-        used |= ctxInTile;
-        std::vector<int> cand;
-        for (int pos = 0; pos < tileBits; ++pos) {
-            if (!((used >> pos) & 1u)) cand.push_back(pos);
-        }
-        if (cand.size() < 3) return false;
-        // fragment shape with the fewest bank conflicts: the quarter-warps of a B load differ in (sigma0, sigma1, kappa0),
-        // those of a D store in (kappa1, kappa2, sigma0)
-        auto ways = [](int a, int b, int c) {
-            int count8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            int worst = 0;
-            for (uint32_t m = 0; m < 8; ++m) {
-                const uint32_t t = ((m & 1u) << a) | (((m >> 1) & 1u) << b) | (((m >> 2) & 1u) << c);
-                worst = std::max(worst, ++count8[swz(t) & 7u]);
+    }
+    auto planBlocks = [&](uint32_t warpBits) -> bool {
+    for (int i = 0; i < count; ++i) {
+            const DenseBlock& blk = *blocks[i];
+            BlockDesc& d = pass.blocks[i];
+            const int k = blk.k();
+            if (k != 3 && k != 4) return false;
+            if (static_cast<int>(blk.ctx.size()) > kBlockMaxCtx) return false;
+            d.k = k;
+            d.nCtx = static_cast<uint8_t>(blk.ctx.size());
+            uint32_t used = 0; // tile bits that cannot be fragment columns: targets and in-tile context bits
+            std::array<int, 4> tp{};
+            for (int t = 0; t < k; ++t) {
+                tp[static_cast<std::size_t>(t)] = tilePos(blk.targets[static_cast<std::size_t>(t)]);
+                if (tp[static_cast<std::size_t>(t)] < 0) return false;
+                used |= 1u << tp[static_cast<std::size_t>(t)];
             }
-            return worst;
-        };
-        int best = 1 << 30;
-        int bs0 = 0, bs1 = 1, bk0 = 0, bk1 = 1, bk2 = 2;
-        for (int s0 = 0; s0 < k; ++s0) {
-            for (int s1 = 0; s1 < k; ++s1) {
-                if (s1 == s0) continue;
-                for (std::size_t a = 0; a < cand.size(); ++a) {
-                    const int wB = ways(tp[static_cast<std::size_t>(s0)], tp[static_cast<std::size_t>(s1)], cand[a]);
-                    if (wB * 16 >= best) continue;
-                    for (std::size_t b1 = 0; b1 < cand.size(); ++b1) {
-                        if (b1 == a) continue;
-                        for (std::size_t b2 = b1 + 1; b2 < cand.size(); ++b2) { // (kappa1, kappa2) is symmetric for the conflict count
-                            if (b2 == a) continue;
-                            const int wD = ways(cand[b1], cand[b2], tp[static_cast<std::size_t>(s0)]);
-                            const int score = wB * 16 + wD;
-                            if (score < best) {
-                                best = score;
-                                bs0 = s0;
-                                bs1 = s1;
-                                bk0 = cand[a];
-                                bk1 = cand[b1];
-                                bk2 = cand[b2];
+            uint32_t ctxInTile = 0;
+            for (std::size_t j = 0; j < blk.ctx.size(); ++j) {
+                const int q = blk.ctx[j];
+                const int pos = tilePos(q);
+                if (pos >= 0) {
+                    d.ctxSrc[j] = static_cast<uint8_t>(pos);
+                    ctxInTile |= 1u << pos;
+                } else {
+                    d.ctxSrc[j] = static_cast<uint8_t>(32 + (q - kLaneBits));
+                }
+            }
+            used |= ctxInTile;
+            std::vector<int> cand;
+            for (int pos = 0; pos < tileBits; ++pos) {
+                if (!((used >> pos) & 1u) && !((warpBits >> pos) & 1u)) cand.push_back(pos);
+            }
+            if (cand.size() < 3) return false;
+            // fragment shape with the fewest bank conflicts: the quarter-warps of a B load differ in (sigma0, sigma1, kappa0),
+            // those of a D store in (kappa1, kappa2, sigma0)
+            auto ways = [](int a, int b, int c) {
+                int count8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                int worst = 0;
+                for (uint32_t m = 0; m < 8; ++m) {
+                    const uint32_t t = ((m & 1u) << a) | (((m >> 1) & 1u) << b) | (((m >> 2) & 1u) << c);
+                    worst = std::max(worst, ++count8[swz(t) & 7u]);
+                }
+                return worst;
+            };
+            int best = 1 << 30;
+            int bs0 = 0, bs1 = 1, bk0 = 0, bk1 = 1, bk2 = 2;
+            for (int s0 = 0; s0 < k; ++s0) {
+                for (int s1 = 0; s1 < k; ++s1) {
+                    if (s1 == s0) continue;
+                    for (std::size_t a = 0; a < cand.size(); ++a) {
+                        const int wB = ways(tp[static_cast<std::size_t>(s0)], tp[static_cast<std::size_t>(s1)], cand[a]);
+                        if (wB * 16 >= best) continue;
+                        for (std::size_t b1 = 0; b1 < cand.size(); ++b1) {
+                            if (b1 == a) continue;
+                            for (std::size_t b2 = b1 + 1; b2 < cand.size(); ++b2) { // (kappa1, kappa2) is symmetric for the conflict count
+                                if (b2 == a) continue;
+                                const int wD = ways(cand[b1], cand[b2], tp[static_cast<std::size_t>(s0)]);
+                                const int score = wB * 16 + wD;
+                                if (score < best) {
+                                    best = score;
+                                    bs0 = s0;
+                                    bs1 = s1;
+                                    bk0 = cand[a];
+                                    bk1 = cand[b1];
+                                    bk2 = cand[b2];
+                                }
                             }
                         }
                     }
                 }
             }
-        }
-        d.conflictWays = static_cast<uint8_t>(std::max(best / 16, best % 16));
-        // sigma order: the two chosen targets first, the others ascending
-        std::array<int, 4> order{};
-        order[0] = bs0;
-        order[1] = bs1;
-        int at = 2;
-        for (int t = 0; t < k; ++t) {
-            if (t != bs0 && t != bs1) order[static_cast<std::size_t>(at++)] = t;
-        }
-        for (int i2 = 0; i2 < k; ++i2) d.sigma[i2] = static_cast<uint8_t>(tp[static_cast<std::size_t>(order[static_cast<std::size_t>(i2)])]);
-        for (int s = 0; s < (1 << k); ++s) {
-            int canon = 0;
-            for (int i2 = 0; i2 < k; ++i2) {
-                if ((s >> i2) & 1) canon |= 1 << order[static_cast<std::size_t>(i2)];
+            d.conflictWays = static_cast<uint8_t>(std::max(best / 16, best % 16));
+            // sigma order: the two chosen targets first, the others ascending
+            std::array<int, 4> order{};
+            order[0] = bs0;
+            order[1] = bs1;
+            int at = 2;
+            for (int t = 0; t < k; ++t) {
+                if (t != bs0 && t != bs1) order[static_cast<std::size_t>(at++)] = t;
             }
-            d.canon[s] = static_cast<uint8_t>(canon);
+            for (int i2 = 0; i2 < k; ++i2) d.sigma[i2] = static_cast<uint8_t>(tp[static_cast<std::size_t>(order[static_cast<std::size_t>(i2)])]);
+            for (int s = 0; s < (1 << k); ++s) {
+                int canon = 0;
+                for (int i2 = 0; i2 < k; ++i2) {
+                    if ((s >> i2) & 1) canon |= 1 << order[static_cast<std::size_t>(i2)];
+                }
+                d.canon[s] = static_cast<uint8_t>(canon);
+            }
+            d.kappa[0] = static_cast<uint8_t>(bk0);
+            d.kappa[1] = static_cast<uint8_t>(bk1);
+            d.kappa[2] = static_cast<uint8_t>(bk2);
+            // unit bits: every other tile bit, context bits last
+            int nu = 0;
+            const uint32_t taken = used | (1u << bk0) | (1u << bk1) | (1u << bk2);
+            for (int pos = 0; pos < tileBits; ++pos) {
+                if (!((taken >> pos) & 1u) && !((warpBits >> pos) & 1u)) d.unitPos[nu++] = static_cast<uint8_t>(pos);
+            }
+            for (int pos = 0; pos < tileBits; ++pos) {
+                if (((ctxInTile >> pos) & 1u) && !((warpBits >> pos) & 1u)) d.unitPos[nu++] = static_cast<uint8_t>(pos);
+            }
+            for (int pos = 0; pos < tileBits; ++pos) { // the warp bits on top, in the same order for every block
+                if ((warpBits >> pos) & 1u) d.unitPos[nu++] = static_cast<uint8_t>(pos);
+            }
+            if (nu != tileBits - k - 3) return false;
+            d.unitBit0IsCtx = (nu > 0 && ((ctxInTile >> d.unitPos[0]) & 1u)) ? 1 : 0;
+            d.nUnitBits = static_cast<uint8_t>(nu);
+            d.nUnits = 1 << nu;
         }
-        d.kappa[0] = static_cast<uint8_t>(bk0);
-        d.kappa[1] = static_cast<uint8_t>(bk1);
-        d.kappa[2] = static_cast<uint8_t>(bk2);
-        // unit bits: every other tile bit, context bits last
-        int nu = 0;
-        const uint32_t taken = used | (1u << bk0) | (1u << bk1) | (1u << bk2);
-        for (int pos = 0; pos < tileBits; ++pos) {
-            if (!((taken >> pos) & 1u)) d.unitPos[nu++] = static_cast<uint8_t>(pos);
+        return true;
+    };
+    uint32_t warpBits = 0;
+    if (count > 1) {
+        int have = 0;
+        for (int pos = tileBits - 1; pos >= 0 && have < 3; --pos) {
+            if (!((allTargets >> pos) & 1u)) {
+                warpBits |= 1u << pos;
+                ++have;
+            }
         }
-        for (int pos = 0; pos < tileBits; ++pos) {
-            if ((ctxInTile >> pos) & 1u) d.unitPos[nu++] = static_cast<uint8_t>(pos);
-        }
-        if (nu != tileBits - k - 3) return false;
-        d.unitBit0IsCtx = (nu > 0 && ((ctxInTile >> d.unitPos[0]) & 1u)) ? 1 : 0;
-        d.nUnitBits = static_cast<uint8_t>(nu);
-        d.nUnits = 1 << nu;
+        if (have < 3) warpBits = 0;
     }
-    return true;
+    if (warpBits != 0 && planBlocks(warpBits)) {
+        pass.warpLocal = 1;
+        return true;
+    }
+    pass.warpLocal = 0;
+    return planBlocks(0);
 }
 
 } // namespace fddb200

@@ -362,8 +362,9 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
         const int mw = warp - kComputeWarps;
         const double2* __restrict__ y = static_cast<const double2*>(p.y);
         double2* __restrict__ z = static_cast<double2*>(p.z);
-        auto copyIn = [&](int it) {
-            double2* dst = tiles + static_cast<size_t>(it % nBuffers) * tileElems;
+        // (buffer index and barrier phase of iteration `it` are passed in: no division in the loop)
+        auto copyIn = [&](int it, int buf) {
+            double2* dst = tiles + static_cast<size_t>(buf) * tileElems;
             const double2* src = y + (static_cast<uint64_t>(tileSeg[it]) << kLaneBits) + lane;
             if (!(p.debugSkip & 2u)) {
 #pragma unroll 4
@@ -372,12 +373,12 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
                     cp_async16(dst + (e.y ^ laneSwz), src + (static_cast<uint64_t>(e.x) << kLaneBits));
                 }
             }
-            mbarArriveOnCopies(full + it % nBuffers);
+            mbarArriveOnCopies(full + buf);
         };
-        auto copyOut = [&](int it) {
-            mbarWait(done + it % nBuffers, static_cast<unsigned>(it / nBuffers) & 1u);
+        auto copyOut = [&](int it, int buf, unsigned phase) {
+            mbarWait(done + buf, phase);
             if (p.debugSkip & 2u) return;
-            const double2* src = tiles + static_cast<size_t>(it % nBuffers) * tileElems;
+            const double2* src = tiles + static_cast<size_t>(buf) * tileElems;
             double2* dst = z + (static_cast<uint64_t>(tileSeg[it]) << kLaneBits) + lane;
 #pragma unroll 4
             for (uint32_t j = mw; j < nSegTile; j += kMemoryWarps) {
@@ -386,18 +387,27 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
             }
         };
         int it = 0;
+        int buf = 0, prevBuf = 0;          // buffers of tile `it` and of tile `it - 1`
+        unsigned prevPhase = 0;            // barrier phase of tile `it - 1`: (it - 1) / nBuffers & 1
+        unsigned phase = 0;
         for (uint32_t t = blockIdx.x;; ++it, t += gridDim.x) {
             const bool haveNext = t < p.nTiles;
             const bool havePrev = it > 0;
             if (!haveNext && !havePrev) break;
             if (nBuffers == 1) { // the only buffer: out before in
-                if (havePrev) copyOut(it - 1);
-                if (haveNext) copyIn(it);
+                if (havePrev) copyOut(it - 1, prevBuf, prevPhase);
+                if (haveNext) copyIn(it, buf);
             } else {
-                if (haveNext) copyIn(it);
-                if (havePrev) copyOut(it - 1);
+                if (haveNext) copyIn(it, buf);
+                if (havePrev) copyOut(it - 1, prevBuf, prevPhase);
             }
             if (!haveNext) break;
+            prevBuf = buf;
+            prevPhase = phase;
+            if (++buf == nBuffers) {
+                buf = 0;
+                phase ^= 1u;
+            }
         }
         cp_async_wait<0>();
     } else {
@@ -418,13 +428,15 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
             bool anyCtxOut = false;
             for (int j = 0; j < p.blocks[0].nCtx; ++j) anyCtxOut = anyCtxOut || p.blocks[0].ctxSrc[j] >= 32u;
             int it = 0;
+            int buf = 0;
+            unsigned phase = 0;
             long long cWait = 0, cRun = 0;
             const long long cStart = clock64();
             for (uint32_t t = blockIdx.x; t < p.nTiles; t += gridDim.x, ++it) {
-                double2* tile = tiles + static_cast<size_t>(it % nBuffers) * tileElems;
+                double2* tile = tiles + static_cast<size_t>(buf) * tileElems;
                 const uint32_t ctxOut = anyCtxOut ? ctxOutOf(p.blocks[0], tileSeg[it]) : 0u;
                 const long long c0 = p.debugClocks != nullptr ? clock64() : 0;
-                mbarWait(full + it % nBuffers, static_cast<unsigned>(it / nBuffers) & 1u);
+                mbarWait(full + buf, phase);
                 const long long c1 = p.debugClocks != nullptr ? clock64() : 0;
                 if (!(p.debugSkip & 1u)) runner.run(tile, unitTabs, ctxOut);
                 __syncwarp();
@@ -432,7 +444,11 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
                     cWait += c1 - c0;
                     cRun += clock64() - c1;
                 }
-                if (lane == 0) mbarArrive(done + it % nBuffers); // release: this warp's writes to the tile are visible to the waiters
+                if (lane == 0) mbarArrive(done + buf); // release: this warp's writes to the tile are visible to the waiters
+                if (++buf == nBuffers) {
+                    buf = 0;
+                    phase ^= 1u;
+                }
             }
             if (p.debugClocks != nullptr && lane == 0) {
                 long long* out = p.debugClocks + (static_cast<size_t>(blockIdx.x) * kComputeWarps + warp) * 4;
@@ -448,14 +464,21 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
             return;
         }
         int it = 0;
+        int buf = 0;
+        unsigned phase = 0;
         for (uint32_t t = blockIdx.x; t < p.nTiles; t += gridDim.x, ++it) {
-            double2* tile = tiles + static_cast<size_t>(it % nBuffers) * tileElems;
-            mbarWait(full + it % nBuffers, static_cast<unsigned>(it / nBuffers) & 1u);
+            double2* tile = tiles + static_cast<size_t>(buf) * tileElems;
+            mbarWait(full + buf, phase);
             const uint32_t segBase = tileSeg[it];
             for (int g = 0; g < p.nBlocks && !(p.debugSkip & 1u); ++g) {
                 const BlockDesc& b = p.blocks[g];
                 const uint32_t ctxOut = ctxOutOf(b, segBase);
-                if (g > 0) asm volatile("bar.sync 1, %0;\n" ::"n"(32 * kComputeWarps) : "memory"); // the previous block has written the whole tile
+                if (g > 0) {
+                    // the previous block has written what this one reads: this warp's own eighth of the tile when the pass is
+                    // warp local, else anywhere in the tile
+                    if (p.warpLocal) __syncwarp();
+                    else asm volatile("bar.sync 1, %0;\n" ::"n"(32 * kComputeWarps) : "memory");
+                }
                 if (b.k == 4) {
                     BlockRunner<4, kComputeWarps, FDD_BLOCK_PREFETCH != 0> runner;
                     runner.init(b, laneTabs + g * 32 * 8, warp, lane);
@@ -467,7 +490,11 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
                 }
             }
             __syncwarp();
-            if (lane == 0) mbarArrive(done + it % nBuffers); // release: this warp's writes to the tile are visible to the waiters
+            if (lane == 0) mbarArrive(done + buf); // release: this warp's writes to the tile are visible to the waiters
+            if (++buf == nBuffers) {
+                buf = 0;
+                phase ^= 1u;
+            }
         }
     }
 }

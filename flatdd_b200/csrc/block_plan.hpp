@@ -92,6 +92,9 @@ struct PassParams {
     uint32_t tileMask;      // segment-index bits (relative to the segment index = amplitude index >> 5) inside the tile
     uint32_t nTiles;
     uint32_t rankSegBits;   // rank << (nLocal - 5): the global (shard) bits of every segment index
+    uint32_t warpLocal;     // 1: the top three unit bits of EVERY block are the same three tile bits, none of them a target of any block:
+                            // compute warp w (of eight) touches the same eighth of the tile in every block, so the blocks of a pass need
+                            // no barrier between them, only the warp's own order
     uint32_t debugSkip;     // experiments (FLATDD_B200_BLOCK_SKIP): bit 0 = no tensor-core work, bit 1 = no global loads/stores
     long long* debugClocks; // experiments (FLATDD_B200_BLOCK_CLOCKS): per compute warp {cycles waiting for tiles, cycles in the blocks, total}
     BlockDesc blocks[kPassMaxBlocks];

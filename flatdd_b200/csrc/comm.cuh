@@ -102,6 +102,71 @@ __global__ void __launch_bounds__(256) exchange_p2p_kernel(const double2* __rest
     }
 }
 
+// ---- the same exchange with its own cross-GPU ordering (no NCCL call on the data path) -----------------------------------
+// Each rank owns two epoch words in peer-mapped memory: flags[0] = "everything I launched before exchange e has completed: my
+// current buffer holds the state", flags[1] = "I have finished reading my partner's buffer in exchange e".  The kernel
+//   1. publishes flags[0] = e (it runs after the rank's earlier launches, so their writes are complete) and waits for the
+//      partner's flags[0] >= e before it touches the partner's buffer;
+//   2. copies (same body as above);
+//   3. its last CTA publishes flags[1] = e and does not exit before the partner's flags[1] >= e: the next launch of this
+//      rank's stream overwrites the buffer the partner has been reading.
+// Replaces two stream-ordered one-element ncclAllReduce "barriers" (about 55 us of the 164 us per exchange at 8 GPUs and
+// 64 MiB messages).  Epochs only grow; every rank takes part in every exchange, so they agree on e.
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+template <int U>
+__global__ void __launch_bounds__(256) exchange_p2p_flag_kernel(const double2* __restrict__ mine, const double2* __restrict__ partner,
+                                                                double2* __restrict__ out, uint64_t n, int pl, int myBit, uint32_t* myFlags,
+                                                                const uint32_t* partnerFlags, uint32_t epoch, unsigned int* ctaCounter) {
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) st_release_sys(myFlags, epoch);
+        while (ld_acquire_sys(partnerFlags) < epoch) __nanosleep(64);
+    }
+    __syncthreads();
+    const uint64_t half = n >> 1;
+    const uint64_t lowMask = (uint64_t{1} << pl) - 1;
+    const uint64_t keepBit = static_cast<uint64_t>(myBit) << pl;
+    const uint64_t flip = uint64_t{1} << pl;
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    uint64_t h = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (; h + (U - 1) * stride < half; h += U * stride) {
+        double2 far[U], near[U];
+        uint64_t at[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t x = h + u * stride;
+            at[u] = ((x & ~lowMask) << 1) | (x & lowMask) | keepBit;
+            far[u] = ld_stream(partner + at[u]); // crosses NVLink
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) near[u] = ld_stream(mine + at[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            st_stream(out + at[u], near[u]);
+            st_stream(out + (at[u] ^ flip), far[u]);
+        }
+    }
+    for (; h < half; h += stride) {
+        const uint64_t i = ((h & ~lowMask) << 1) | (h & lowMask) | keepBit;
+        out[i] = mine[i];
+        out[i ^ flip] = partner[i];
+    }
+    __syncthreads(); // every load of this CTA has returned (its value was stored)
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int arrived = atomicAdd(ctaCounter, 1u);
+        if (arrived == gridDim.x - 1) {
+            *ctaCounter = 0; // for the next exchange (every CTA has arrived)
+            st_release_sys(myFlags + 1, epoch);
+            while (ld_acquire_sys(partnerFlags + 1) < epoch) __nanosleep(64);
+        }
+    }
+}
+
 // local SWAP of two physical bits (a < b), out of place; used by the NCCL path to bring `pl` to the top
 __global__ void __launch_bounds__(256) swap_local_bits_kernel(const double2* __restrict__ in, double2* __restrict__ out, uint64_t n,
                                                               int a, int b) {

@@ -175,6 +175,65 @@ private:
     int32_t records_ = 0;
 };
 
+// Queues consecutive apply() calls and hands them to the wrapped backend in one applyMany() (so the GPU library can keep the state
+// tile-resident across consecutive dense blocks); anything else flushes the queue first.
+class BatchingBackend final : public ArrayBackend {
+public:
+    explicit BatchingBackend(ArrayBackend* inner, std::size_t maxQueued = 64) : inner_(inner), maxQueued_(maxQueued) {}
+    ~BatchingBackend() override {
+        try {
+            flush();
+        } catch (...) {
+        }
+    }
+    void convert(const FlatVecDD& dd) override {
+        flush();
+        inner_->convert(dd);
+    }
+    void apply(const FlatMatDD& gate, int nOriginalGates) override {
+        gates_.push_back(gate);
+        originals_.push_back(nOriginalGates);
+        if (gates_.size() >= maxQueued_) flush();
+    }
+    void applyMany(const std::vector<FlatMatDD>& gates, const std::vector<int>& nOriginalGates) override {
+        flush();
+        inner_->applyMany(gates, nOriginalGates);
+    }
+    void getState(double* real, double* imag) override {
+        flush();
+        inner_->getState(real, imag);
+    }
+    void synchronize() override {
+        flush();
+        inner_->synchronize();
+    }
+    void exchange(int globalPhysicalBit, int localPhysicalBit) override {
+        flush();
+        inner_->exchange(globalPhysicalBit, localPhysicalBit);
+    }
+    void relabel(int a, int b) override {
+        flush();
+        inner_->relabel(a, b);
+    }
+    void canonicalize() override {
+        flush();
+        inner_->canonicalize();
+    }
+    double lastKernelMs() override { return inner_->lastKernelMs(); }
+    void flush() {
+        if (gates_.empty()) return;
+        inner_->applyMany(gates_, originals_);
+        gates_.clear();
+        originals_.clear();
+    }
+
+private:
+    ArrayBackend* inner_;
+    std::size_t maxQueued_;
+    std::vector<FlatMatDD> gates_;
+    std::vector<int> originals_;
+};
+
 class TeeBackend final : public ArrayBackend {
 public:
     explicit TeeBackend(std::vector<ArrayBackend*> sinks) : sinks_(std::move(sinks)) {}

@@ -66,7 +66,7 @@ struct FusionPolicy {
     // pass over the state (consecutive blocks the library applies to a resident shared-memory tile) have at most passUpper
     // target qubits above the five warp-lane qubits between them (a 2^12-amplitude tile) and number at most passBlocks
     int blockTargets = 4;
-    int blockContext = 6;
+    int blockContext = 5;   // (every context qubit doubles the table of a block: 5 keeps the fusion pass below 0.1 s on dnn_n25, 6 takes 0.2 s for 14 % fewer blocks)
     int passUpper = 7;
     int passBlocks = 1; // (1: blocks are formed without regard to their neighbours — measured best: fewest blocks; the library still shares passes where neighbours happen to fit)
 };
@@ -860,7 +860,52 @@ private:
                         passUpperSet.clear();
                         passBlocks = 0;
                     } else if (!memo[i].gate.isIdentity()) {
-                        block.apply(memo[i].gate);
+                        // A run of one-qubit operations on the same qubit (u3 = rz ry rz, ...) is multiplied as 2 x 2 matrices first
+                        // and reaches the block's table once.  Only operations that the selection rule above would take next anyway
+                        // are absorbed: they follow on the same qubit, wait for nothing else and do not grow the block.
+                        const SmallGate& g0 = memo[i].gate;
+                        std::size_t tail = i; // last absorbed operation: its successors are released below
+                        if (g0.targets.size() + g0.ctx.size() == 1) {
+                            const int pq = g0.targets.empty() ? g0.ctx[0] : g0.targets[0];
+                            std::vector<int> t2, c2;
+                            block.merged(g0, t2, c2);
+                            const bool isTarget = std::binary_search(t2.begin(), t2.end(), pq);
+                            std::array<cplx, 4> m = as2x2(g0);
+                            for (;;) {
+                                if (succ[tail].size() != 1) break;
+                                const std::size_t j = succ[tail][0];
+                                if (indeg[j] != 1 || (worldSize > 1 && DdOps::isRelabelSwap(*ops[first + j]))) break;
+                                if (!haveMemo[j]) {
+                                    memo[j] = opBlockFor(ops[first + j].get(), &s.pending);
+                                    haveMemo[j] = 1;
+                                }
+                                const SmallGate& gj = memo[j].gate;
+                                if (!memo[j].isBlock || gj.targets.size() + gj.ctx.size() != 1) break;
+                                if ((gj.targets.empty() ? gj.ctx[0] : gj.targets[0]) != pq) break;
+                                if (!gj.targets.empty() && !isTarget) break; // would turn a context qubit into a target: the selection rule decides that
+                                const std::array<cplx, 4> mj = as2x2(gj);
+                                m = {mj[0] * m[0] + mj[1] * m[2], mj[0] * m[1] + mj[1] * m[3], mj[2] * m[0] + mj[3] * m[2], mj[2] * m[1] + mj[3] * m[3]};
+                                --indeg[j]; // (== 0: taken right here, never enters the ready list)
+                                ++done;
+                                ++blockOps;
+                                tail = j;
+                            }
+                            const SmallGate fused = from2x2(pq, m);
+                            if (!fused.isIdentity()) block.apply(fused);
+                        } else {
+                            block.apply(g0);
+                        }
+                        if (tail != i) {
+                            for (std::size_t nxt : succ[tail]) {
+                                if (--indeg[nxt] == 0) ready.insert(std::lower_bound(ready.begin(), ready.end(), nxt), nxt);
+                            }
+                            ++blockOps;
+                            ++done;
+                            // i itself leaves the ready list; its only successor was absorbed
+                            ready.erase(std::find(ready.begin(), ready.end(), i));
+                            progress = true;
+                            continue;
+                        }
                     }
                     if (!emittedRaw) ++blockOps;
                     ready.erase(ready.begin() + static_cast<long>(r));
@@ -893,6 +938,25 @@ private:
         return s;
     }
     std::unordered_map<std::string, OpBlock> opBlockCache;
+    // a one-qubit block as a dense 2 x 2 matrix and back (diagonal matrices go back as context-only blocks, the identity as the scalar 1)
+    static std::array<cplx, 4> as2x2(const SmallGate& g) {
+        if (!g.targets.empty()) return {g.table[0], g.table[1], g.table[2], g.table[3]};
+        if (!g.ctx.empty()) return {g.table[0], cplx(0, 0), cplx(0, 0), g.table[1]};
+        return {g.table[0], cplx(0, 0), cplx(0, 0), g.table[0]};
+    }
+    static SmallGate from2x2(int q, const std::array<cplx, 4>& m) {
+        SmallGate g;
+        if (m[1] != cplx(0, 0) || m[2] != cplx(0, 0)) {
+            g.targets = {q};
+            g.table.assign(m.begin(), m.end());
+        } else if (m[0] != m[3]) {
+            g.ctx = {q};
+            g.table = {m[0], m[3]};
+        } else {
+            g.table = {m[0]};
+        }
+        return g;
+    }
 
     void execute(const Schedule& s) {
         if (verbose) {

@@ -18,8 +18,16 @@ using cplx = std::complex<double>;
 
 namespace {
 
-template <int K> void applyBlockEmu(const BlockDesc& b, const double* table, std::vector<cplx>& tile, uint32_t segBaseWithRank, int* worstConflict) {
+// owner: per 16-byte slot of the tile the compute warp (of eight) that touched it in an earlier block of a warp-local pass
+template <int K> void applyBlockEmu(const BlockDesc& b, const double* table, std::vector<cplx>& tile, uint32_t segBaseWithRank, int* worstConflict,
+                                    std::vector<int>* owner, int* violations) {
     constexpr int ROWS = 1 << K, MT = ROWS / 8, KTL = ROWS / 4;
+    auto claim = [&](uint32_t at, uint32_t unit) {
+        if (owner == nullptr) return;
+        const int w = static_cast<int>(unit / (static_cast<uint32_t>(b.nUnits) / 8u));
+        if ((*owner)[at] >= 0 && (*owner)[at] != w) ++*violations;
+        (*owner)[at] = w;
+    };
     for (uint32_t u = 0; u < static_cast<uint32_t>(b.nUnits); ++u) {
         const uint32_t off = unitOff(b, u);
         const uint32_t ctx = ctxIndex(b, off, segBaseWithRank);
@@ -33,6 +41,7 @@ template <int K> void applyBlockEmu(const BlockDesc& b, const double* table, std
                 const uint32_t at = pu ^ swz(laneOffB(b, lane)) ^ swz(ktOff(b, kt));
                 if (at != swz(off | laneOffB(b, lane) | ktOff(b, kt))) std::fprintf(stderr, "emu: swizzle pieces do not combine\n");
                 y[kt][lane] = tile[at];
+                claim(at, u);
                 ++hits[lane >> 3][at & 7u];
             }
             for (auto& q : hits) {
@@ -63,6 +72,8 @@ template <int K> void applyBlockEmu(const BlockDesc& b, const double* table, std
                 const uint32_t at = pu ^ swz(laneOffD(b, lane)) ^ swz(mtOff(b, mt));
                 tile[at] = d[lane][0];
                 tile[at ^ swz(1u << b.kappa[0])] = d[lane][1];
+                claim(at, u);
+                claim(at ^ swz(1u << b.kappa[0]), u);
                 ++hits[0][lane >> 3][at & 7u];
                 ++hits[1][lane >> 3][(at ^ swz(1u << b.kappa[0])) & 7u];
             }
@@ -81,7 +92,8 @@ extern "C" {
 
 // Applies the gates (flat matrix DDs) as ONE pass to the shard `rank` of an n-qubit state held in (re, im), 2^nLocal
 // amplitudes, in place.  Returns 0, or a negative code: -1 a gate is not a dense block, -2 the pass does not fit.
-// info[0] = worst measured bank-conflict degree, info[1] = worst planned one, info[2] = tile bits used, info[3] = blocks' k packed.
+// info[0] = worst measured bank-conflict degree, info[1] = worst planned one, info[2] = tile bits used, info[3] = blocks' k packed,
+// info[4] = the planner declared the pass warp local, info[5] = tile slots that two different compute warps touched in a warp-local pass.
 int emu_apply_pass(const fdd_matdd* gates, int count, int nLocal, int rank, int tileBits, double* re, double* im, int* info) {
     std::vector<DenseBlock> blocks(static_cast<size_t>(count));
     std::vector<const DenseBlock*> ptrs;
@@ -98,6 +110,8 @@ int emu_apply_pass(const fdd_matdd* gates, int count, int nLocal, int rank, int 
     info[1] = 0;
     info[2] = p.tileBits;
     info[3] = 0;
+    info[4] = static_cast<int>(p.warpLocal);
+    info[5] = 0;
     for (int g = 0; g < count; ++g) {
         info[1] = std::max<int>(info[1], p.blocks[g].conflictWays);
         info[3] = info[3] * 10 + p.blocks[g].k;
@@ -110,13 +124,15 @@ int emu_apply_pass(const fdd_matdd* gates, int count, int nLocal, int rank, int 
             const uint64_t seg = segBase | pdep32(j, p.tileMask);
             for (uint32_t lane = 0; lane < 32; ++lane) tile[swz(j * 32u + lane)] = cplx(re[(seg << 5) + lane], im[(seg << 5) + lane]);
         }
+        std::vector<int> owner(tile.size(), -1);
         for (int g = 0; g < count; ++g) {
             const BlockDesc& b = p.blocks[g];
             const double* table = blocks[static_cast<size_t>(g)].table.data();
+            std::vector<int>* own = (p.warpLocal && b.nUnits >= 8) ? &owner : nullptr;
             if (b.k == 4) {
-                applyBlockEmu<4>(b, table, tile, p.rankSegBits | segBase, &info[0]);
+                applyBlockEmu<4>(b, table, tile, p.rankSegBits | segBase, &info[0], own, &info[5]);
             } else {
-                applyBlockEmu<3>(b, table, tile, p.rankSegBits | segBase, &info[0]);
+                applyBlockEmu<3>(b, table, tile, p.rankSegBits | segBase, &info[0], own, &info[5]);
             }
         }
         for (uint32_t j = 0; j < nSegTile; ++j) {

@@ -36,7 +36,7 @@ def emu():
 
 def run_pass(lib, gates, n_local, rank, tile_bits, re, im):
     arr = (CMatDD * len(gates))(*[g.as_c() for g in gates])
-    info = (ctypes.c_int * 4)()
+    info = (ctypes.c_int * 6)()
     re = np.ascontiguousarray(re).copy()
     im = np.ascontiguousarray(im).copy()
     rc = lib.emu_apply_pass(arr, len(gates), n_local, rank, tile_bits, re.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
@@ -153,6 +153,26 @@ def test_several_blocks_in_one_pass(emu, sets):
     rc, gr, gi, info = run_pass(emu, gates, N, 0, 12, re, im)
     assert rc == 0
     wr, wi = oracle_apply(gates, re, im)
+    assert max(np.max(np.abs(gr - wr)), np.max(np.abs(gi - wi))) < 1e-14
+    assert info[5] == 0  # a warp-local pass keeps every compute warp inside its own eighth of the tile
+
+
+def test_warp_local_passes(emu):
+    """Blocks whose targets leave three tile bits free: every block's top unit bits are those bits, so compute warp w only ever
+    touches the tile slots with those bits == w and no barrier is needed between the blocks."""
+    rng = np.random.default_rng(77)
+    sets = ([5, 6, 7, 8], [8, 9, 0, 1], [2, 3, 6])  # union: 0,1,2,3,5,6,7,8,9 -> bits 4, 10, 11 are free
+    gates = [B.gate_dd(N, s, B.random_unitary(len(s), rng)) for s in sets]
+    re, im = B.random_state(N, rng)
+    rc, gr, gi, info = run_pass(emu, gates, N, 0, 12, re, im)
+    assert rc == 0 and info[4] == 1 and info[5] == 0
+    wr, wi = oracle_apply(gates, re, im)
+    assert max(np.max(np.abs(gr - wr)), np.max(np.abs(gi - wi))) < 1e-14
+    # every tile bit is some block's target: the pass needs barriers
+    full = [B.gate_dd(N, s, B.random_unitary(4, rng)) for s in ([0, 1, 2, 3], [4, 5, 6, 7], [8, 9, 10, 11])]
+    rc, gr, gi, info = run_pass(emu, full, N, 0, 12, re, im)
+    assert rc == 0 and info[4] == 0
+    wr, wi = oracle_apply(full, re, im)
     assert max(np.max(np.abs(gr - wr)), np.max(np.abs(gi - wi))) < 1e-14
 
 
