@@ -45,7 +45,8 @@ def test_trace_replay(case):
             idx, sr, si = G.samples(case, G.TRAVEL)
             got = ctx.get_amplitudes_at(idx)
             assert float(np.max(np.abs(got - (sr + 1j * si)))) < AMP_TOL
-            assert abs(ctx.norm2() - m["reference"]["norm2"]) < 1e-9
+            # (the reference norm in the manifest is a naive fp64 sum over 2^31 terms in oracle/ref_dump.cpp: good to ~1e-8 only)
+            assert abs(ctx.norm2() - m["reference"]["norm2"]) < 1e-8 and abs(ctx.norm2() - 1.0) < 1e-9
             return
         re, im = ctx.get_state()
     _check(case, re, im)

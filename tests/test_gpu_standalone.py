@@ -42,7 +42,8 @@ def test_standalone_final_state(name, golden, fuse):
     assert G.max_amp_err(re, im, fr, fi) < 1e-10
     assert 1.0 - G.fidelity(re, im, fr, fi) < 1e-10
     stats = full["statistics"]
-    assert stats["gpu_kernel_launches"] >= stats["array_phase_launches"] + 1 and stats["applied_gates"] == G.manifest(golden)["n_ops"]
+    # (consecutive dense blocks share a pass over the state: fewer kernel launches than fused gates, at least the conversion and one pass)
+    assert 2 <= stats["gpu_kernel_launches"] <= stats["array_phase_launches"] + 2 and stats["applied_gates"] == G.manifest(golden)["n_ops"]
 
 
 TRAVEL = [c for c in G.cases(G.TRAVEL)]
