@@ -2,7 +2,7 @@
 // apps/FlatDD.cpp (reference apps/FlatDD.cpp:20-146): --file --t/-t --fuse --no_cache --beta --thresh
 // --DDSIM_convert --pv --ps, the same stdout markers, the same JSON "statistics" keys and the same
 // ../../log/results/{time,state}/<name>_FlatDD.txt files.  The array phase runs on the GPU through
-// the C-ABI (include/flatdd_b200.h).  Additions: --gpu D (device), --fuse 3 / 4 (GPU cost model: greedy in program order / dependency graph),
+// the C-ABI (include/flatdd_b200.h).  Additions: --gpu D (device), --fuse 3 / 4 / 5 (GPU cost greedy in program order / dense-block fusion / DD-multiply dependency graph),
 // --bin FILE (final state as raw little-endian fp64: real array then imag array), --trace FILE
 // (also record the boundary traffic), --trace-only (record the boundary traffic WITHOUT a device: the host DD phase,
 // the switch rule and the fusion pass run, every flat table that would cross the C-ABI goes to the --trace file; with
@@ -34,7 +34,7 @@ int main(int argc, char** argv) {
         ("t", "num of threads (kept for CLI compatibility; sizes the reference cost model)", cxxopts::value<unsigned int>()->default_value("16"))
         ("ps", "print simulation stats")
         ("file", "simulate a quantum circuit given by file", cxxopts::value<std::string>())
-        ("fuse", "0 off, 1 reference greedy, 2 DATE'19 op count, 3 GPU cost greedy, 4 dependency-graph fusion with the GPU cost model (fastest)", cxxopts::value<unsigned int>()->default_value("0"))
+        ("fuse", "0 off, 1 reference greedy, 2 DATE'19 op count, 3 GPU cost greedy, 4 dense-block fusion for the tile-resident kernel (fastest), 5 dependency-graph fusion by DD multiplication (round 1)", cxxopts::value<unsigned int>()->default_value("0"))
         ("no_cache", "no cache optimization (accepted; the GPU path has no DMAV cache)")
         ("beta", "EMA parameter (parsed and ignored like the reference: beta stays 0.9)", cxxopts::value<double>()->default_value("0.9"))
         ("thresh", "set the threshold", cxxopts::value<double>()->default_value("2"))

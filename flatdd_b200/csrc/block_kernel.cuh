@@ -214,53 +214,79 @@ template <int K, int WARPS, bool PREFETCH> struct BlockRunner {
         haveCtx = ctx;
     }
 
-    __device__ __forceinline__ void run(double2* __restrict__ tile, const uint32_t* __restrict__ unitTab, uint32_t ctxOut) {
-        if (u0 >= u1) return;
-        uint32_t packed = unitTab[u0];
-        double2 y[KTL];
+    // tensor-core work of one unit: accumulators <- M * y (three real products)
+    __device__ __forceinline__ void issue(const double2 (&y)[KTL], double (&p1)[MT][2], double (&p2)[MT][2], double (&p3)[MT][2]) {
 #pragma unroll
-        for (int kt = 0; kt < KTL; ++kt) y[kt] = tile[(packed & 0xffffu) ^ pBk[kt]];
-        for (int u = u0; u < u1; ++u) {
-            const uint32_t ctx = (packed >> 16) | ctxOut;
-            if (ctx != haveCtx) loadA(ctx);
-            const uint32_t pu = packed & 0xffffu; // already swizzled
-            // the next unit's inputs (other shared-memory slots than this unit's: no hazard with the stores below)
-            double2 yNext[KTL];
-            uint32_t packedNext = packed;
-            if (PREFETCH && u + 1 < u1) {
-                packedNext = unitTab[u + 1];
+        for (int mt = 0; mt < MT; ++mt) p1[mt][0] = p1[mt][1] = p2[mt][0] = p2[mt][1] = p3[mt][0] = p3[mt][1] = 0.0;
 #pragma unroll
-                for (int kt = 0; kt < KTL; ++kt) yNext[kt] = tile[(packedNext & 0xffffu) ^ pBk[kt]];
-            }
-            double p1[MT][2], p2[MT][2], p3[MT][2];
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) p1[mt][0] = p1[mt][1] = p2[mt][0] = p2[mt][1] = p3[mt][0] = p3[mt][1] = 0.0;
-#pragma unroll
-            for (int kt = 0; kt < KTL; ++kt) {
-                const double ys = y[kt].x + y[kt].y;
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    dmma884(p1[mt], aR[mt][kt], y[kt].x);
-                    dmma884(p2[mt], aI[mt][kt], y[kt].y);
-                    dmma884(p3[mt], aS[mt][kt], ys);
-                }
-            }
-            __syncwarp(); // in place: every lane holds this unit's inputs before any lane overwrites them
+        for (int kt = 0; kt < KTL; ++kt) {
+            const double ys = y[kt].x + y[kt].y;
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-                const uint32_t at = pu ^ pDm[mt];
-                tile[at] = make_double2(p1[mt][0] - p2[mt][0], (p3[mt][0] - p1[mt][0]) - p2[mt][0]);
-                tile[at ^ pK0] = make_double2(p1[mt][1] - p2[mt][1], (p3[mt][1] - p1[mt][1]) - p2[mt][1]);
+                dmma884(p1[mt], aR[mt][kt], y[kt].x);
+                dmma884(p2[mt], aI[mt][kt], y[kt].y);
+                dmma884(p3[mt], aS[mt][kt], ys);
             }
-            if (PREFETCH) {
+        }
+    }
+    __device__ __forceinline__ void finish(double2* __restrict__ tile, uint32_t pu, const double (&p1)[MT][2], const double (&p2)[MT][2], const double (&p3)[MT][2]) {
+        __syncwarp(); // in place: every lane holds this unit's inputs before any lane overwrites them
 #pragma unroll
-                for (int kt = 0; kt < KTL; ++kt) y[kt] = yNext[kt];
-                packed = packedNext;
-            } else if (u + 1 < u1) {
-                packed = unitTab[u + 1];
+        for (int mt = 0; mt < MT; ++mt) {
+            const uint32_t at = pu ^ pDm[mt];
+            tile[at] = make_double2(p1[mt][0] - p2[mt][0], (p3[mt][0] - p1[mt][0]) - p2[mt][0]);
+            tile[at ^ pK0] = make_double2(p1[mt][1] - p2[mt][1], (p3[mt][1] - p1[mt][1]) - p2[mt][1]);
+        }
+    }
+    __device__ __forceinline__ void fetch(const double2* __restrict__ tile, uint32_t packed, double2 (&y)[KTL]) {
 #pragma unroll
-                for (int kt = 0; kt < KTL; ++kt) y[kt] = tile[(packed & 0xffffu) ^ pBk[kt]];
+        for (int kt = 0; kt < KTL; ++kt) y[kt] = tile[(packed & 0xffffu) ^ pBk[kt]];
+    }
+
+    // Software pipeline over the warp's units, two accumulator sets: the tensor-core work of unit u + 1 is issued BEFORE the
+    // subtractions and stores of unit u, and the B fragments of unit u + 2 are fetched meanwhile — the tensor pipe's result
+    // latency (about a hundred cycles) and the shared-memory latency are covered by the warp's own next unit instead of by
+    // other warps (there are only two compute warps per scheduler).
+    __device__ __forceinline__ void run(double2* __restrict__ tile, const uint32_t* __restrict__ unitTab, uint32_t ctxOut) {
+        if (u0 >= u1) return;
+        double2 yA[KTL], yB[KTL];
+        double a1[MT][2], a2[MT][2], a3[MT][2], b1[MT][2], b2[MT][2], b3[MT][2];
+        uint32_t pkA = unitTab[u0], pkB = 0;
+        fetch(tile, pkA, yA);
+        if (u0 + 1 < u1) {
+            pkB = unitTab[u0 + 1];
+            fetch(tile, pkB, yB);
+        }
+        {
+            const uint32_t ctx = (pkA >> 16) | ctxOut;
+            if (ctx != haveCtx) loadA(ctx);
+        }
+        issue(yA, a1, a2, a3);
+        for (int u = u0; u < u1; u += 2) {
+            // accumulators A hold unit u in flight; yB holds the inputs of unit u + 1
+            const uint32_t puA = pkA & 0xffffu;
+            if (u + 1 < u1) {
+                const uint32_t ctx = (pkB >> 16) | ctxOut;
+                if (ctx != haveCtx) loadA(ctx);
+                issue(yB, b1, b2, b3);
             }
+            if (u + 2 < u1) {
+                pkA = unitTab[u + 2];
+                fetch(tile, pkA, yA);
+            }
+            finish(tile, puA, a1, a2, a3);
+            if (u + 1 >= u1) break;
+            const uint32_t puB = pkB & 0xffffu;
+            if (u + 2 < u1) {
+                const uint32_t ctx = (pkA >> 16) | ctxOut;
+                if (ctx != haveCtx) loadA(ctx);
+                issue(yA, a1, a2, a3);
+            }
+            if (u + 3 < u1) {
+                pkB = unitTab[u + 3];
+                fetch(tile, pkB, yB);
+            }
+            finish(tile, puB, b1, b2, b3);
         }
     }
 };
@@ -359,6 +385,9 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
     const uint32_t laneSwz = swz(static_cast<uint32_t>(lane)); // swz is linear: swz(32 j + lane) = swz(32 j) ^ swz(lane)
     if (warp >= kComputeWarps) {
         // =================== memory warps ===================================================================
+        // (they need few registers: hand the rest of the warpgroup's share to the compute warps, whose software pipeline
+        // holds two accumulator sets, two sets of B fragments and the matrix)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
         const int mw = warp - kComputeWarps;
         const double2* __restrict__ y = static_cast<const double2*>(p.y);
         double2* __restrict__ z = static_cast<double2*>(p.z);
@@ -412,6 +441,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
         cp_async_wait<0>();
     } else {
         // =================== compute warps ==================================================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
         auto ctxOutOf = [&](const BlockDesc& b, uint32_t segBase) {
             uint32_t ctxOut = 0;
             for (int j = 0; j < b.nCtx; ++j) {

@@ -20,7 +20,10 @@ CLI = ROOT / "build" / "flatdd_gpu"
 CASES = [("tiny_n3", 1, 0, "tiny_n3_f0"), ("small_n5", 2, 1, "small_n5_f1"), ("mix_n7", 4, 1, "mix_n7_f1"), ("qft_n8", 4, 0, "qft_n8_f0"),
          ("ghz_n6", 4, 0, "ghz_n6_f0"), ("mix_n10", 4, 0, "mix_n10_f0"), ("mix_n10", 4, 1, "mix_n10_f1"), ("mix_n10", 4, 2, "mix_n10_f2"),
          ("mix_n10", 4, 3, "mix_n10_f1"), ("brick_n11", 8, 3, "brick_n11_f1"), ("mix_n12", 8, 1, "mix_n12_f1"), ("mix_n12", 8, 3, "mix_n12_f1"),
-         ("mix_n7", 4, 4, "mix_n7_f1"), ("mix_n10", 4, 4, "mix_n10_f1"), ("brick_n11", 8, 4, "brick_n11_f1"), ("mix_n12", 8, 4, "mix_n12_f1")]
+         ("mix_n7", 4, 4, "mix_n7_f1"), ("mix_n10", 4, 4, "mix_n10_f1"), ("brick_n11", 8, 4, "brick_n11_f1"), ("mix_n12", 8, 4, "mix_n12_f1"),
+         ("compound_n9", 4, 4, "compound_n9_f1"), ("compound_n9", 4, 0, "compound_n9_f0"),
+         # 5: round 1's dependency-graph fusion by DD multiplication
+         ("mix_n10", 4, 5, "mix_n10_f1"), ("mix_n12", 8, 5, "mix_n12_f1")]
 
 
 def run_cli(circuit: Path, threads: int, fuse: int, extra=()):

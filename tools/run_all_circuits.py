@@ -25,8 +25,8 @@ for name in names:
         (Path(tmp) / "log" / "results" / "time").mkdir(parents=True)
         (Path(tmp) / "log" / "results" / "state").mkdir(parents=True)
         t0 = time.perf_counter()
-        # cswap chains: per-gate in the DD-driven binary, like the reference baseline plan (its DD-level fusion of cswap is slow)
-        f = "0" if name.startswith("knn_n31") and not standalone else fuse
+        # (round 1 ran knn_n31 per gate in the DD-driven binary: DD-level fusion of cswap chains was slow; the dense-block fusion is not)
+        f = "0" if name.startswith("knn_n31") and not standalone and fuse in ("1", "2", "3", "5") else fuse
         res = subprocess.run([str(CLI), "--file", str(circuit), "-t", "16", "--fuse", f, "--quiet"] + (["--time-gates"] if "time-gates" in sys.argv[1:] else []), cwd=cwd, capture_output=True, text=True)
         wall = time.perf_counter() - t0
     if res.returncode != 0:
