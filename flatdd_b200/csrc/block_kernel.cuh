@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
     if (threadIdx.x == 0) {
         for (int b = 0; b < nBuffers; ++b) {
             mbarInit(full + b, 32 * kMemoryWarps);
-            mbarInit(done + b, kComputeWarps);
+            mbarInit(done + b, 32 * kComputeWarps); // every compute thread arrives: each one releases its own writes to the tile
         }
     }
     __syncthreads();
@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
                     cWait += c1 - c0;
                     cRun += clock64() - c1;
                 }
-                if (lane == 0) mbarArrive(done + buf); // release: this warp's writes to the tile are visible to the waiters
+                mbarArrive(done + buf); // release: this thread's writes to the tile are visible to the memory warps that wait
                 if (++buf == nBuffers) {
                     buf = 0;
                     phase ^= 1u;
@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
                 }
             }
             __syncwarp();
-            if (lane == 0) mbarArrive(done + buf); // release: this warp's writes to the tile are visible to the waiters
+            mbarArrive(done + buf); // release: this thread's writes to the tile are visible to the memory warps that wait
             if (++buf == nBuffers) {
                 buf = 0;
                 phase ^= 1u;

@@ -575,7 +575,7 @@ private:
                 std::vector<long> preds;
                 for (int q : DdOps::allQubits(*ops[first + i])) {
                     const long pOp = lastOn[static_cast<std::size_t>(q)];
-                    if (pOp >= 0) {
+                    if (pOp >= 0 && pOp != static_cast<long>(i)) { // (a compound operation may list a qubit more than once)
                         bool dup = false;
                         for (long x : preds) dup = dup || x == pOp;
                         if (!dup) preds.push_back(pOp);
@@ -746,7 +746,8 @@ private:
                 std::vector<long> preds;
                 for (int q : DdOps::allQubits(*ops[first + i])) {
                     const long pOp = lastOn[static_cast<std::size_t>(q)];
-                    if (pOp >= 0 && std::find(preds.begin(), preds.end(), pOp) == preds.end()) preds.push_back(pOp);
+                    // (a compound operation lists a qubit once per sub-operation: it is not its own predecessor)
+                    if (pOp >= 0 && pOp != static_cast<long>(i) && std::find(preds.begin(), preds.end(), pOp) == preds.end()) preds.push_back(pOp);
                     lastOn[static_cast<std::size_t>(q)] = static_cast<long>(i);
                 }
                 for (long pOp : preds) {

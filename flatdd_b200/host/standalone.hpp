@@ -936,7 +936,7 @@ private:
                 std::vector<long> preds;
                 for (int q : ops[i]->qubits) {
                     const long p = lastOn[static_cast<std::size_t>(q)];
-                    if (p >= 0 && std::find(preds.begin(), preds.end(), p) == preds.end()) preds.push_back(p);
+                    if (p >= 0 && p != static_cast<long>(i) && std::find(preds.begin(), preds.end(), p) == preds.end()) preds.push_back(p);
                     lastOn[static_cast<std::size_t>(q)] = static_cast<long>(i);
                 }
                 for (long p : preds) {

@@ -15,7 +15,7 @@ ROOT = Path(__file__).resolve().parents[1]
 DUMP = ROOT / "oracle" / "_ref" / "ref_dump"
 
 CASES = [("small_n5", "small_n5_f1", 2), ("mix_n7", "mix_n7_f1", 4), ("qft_n8", "qft_n8_f1", 4), ("mix_n10", "mix_n10_f1", 4), ("brick_n11", "brick_n11_f1", 8),
-         ("mix_n12", "mix_n12_f1", 8)]
+         ("mix_n12", "mix_n12_f1", 8), ("compound_n9", "compound_n9_f1", 4)]
 
 
 @pytest.mark.skipif(not DUMP.exists(), reason="oracle/_ref/ref_dump not built (needs the reference checkout)")
