@@ -130,6 +130,7 @@ struct fdd_ctx {
                                // 2^13 fills the shared memory with one buffer: measured slower than separate passes)
     int blockWarps = 0;       // experiments: 16 = sixteen warps per CTA with one unit per iteration
     int blockUnits = 2;       // units per iteration and warp (2: twelve independent tensor-core chains, one CTA per SM; 1: two CTAs per SM)
+    int blockTablesShared = 1; // multi-block passes keep the blocks' matrix tables in shared memory when they fit
     int blockBuffers = 3;     // tile buffers per CTA when they fit (copy-in, tensor-core work and copy-out of consecutive tiles overlap)
     int blockWs = 1;          // warp-specialised kernel (memory warps + compute warps); 0: every warp loads, computes and stores in turn
     uint64_t blockLaunches = 0;
@@ -554,7 +555,7 @@ bool launchPass(fdd_ctx* c, const fdd_gate* const* gates, int count, bool cacheP
     std::vector<uint64_t> key;
     if (cachePlan) {
         key.reserve(static_cast<size_t>(count) + 1);
-        key.push_back(static_cast<uint64_t>(c->blockTileBits) | (static_cast<uint64_t>(c->blockBuffers) << 8) | (static_cast<uint64_t>(c->blockWarps) << 16) | (static_cast<uint64_t>(c->blockUnits) << 24) | (static_cast<uint64_t>(c->blockWs) << 28));
+        key.push_back(static_cast<uint64_t>(c->blockTileBits) | (static_cast<uint64_t>(c->blockBuffers) << 8) | (static_cast<uint64_t>(c->blockWarps) << 16) | (static_cast<uint64_t>(c->blockUnits) << 24) | (static_cast<uint64_t>(c->blockWs) << 28) | (static_cast<uint64_t>(c->blockTablesShared) << 29));
         for (int i = 0; i < count; ++i) key.push_back(gates[i]->serial);
     }
     fdd_ctx::PlannedPass planned;
@@ -583,18 +584,36 @@ bool launchPass(fdd_ctx* c, const fdd_gate* const* gates, int count, bool cacheP
             // warp-specialised kernel: as many tile buffers as fit (three keep copy-in, tensor work and copy-out in flight)
             planned.grid = static_cast<int>(std::min<uint64_t>(planned.params.nTiles, static_cast<uint64_t>(c->smCount)));
             const uint32_t tilesPerCta = (planned.params.nTiles + static_cast<uint32_t>(planned.grid) - 1) / static_cast<uint32_t>(planned.grid);
+            // a pass of several blocks is bound by its tensor work: two buffers keep the memory warps ahead of it, and the room
+            // of the third one holds the blocks' matrix tables (measured on B200: 0.66 -> 0.62 ms for two 16 x 16 blocks with two
+            // buffers alone; a single-block pass is as fast with two buffers as with three)
+            const int wantBuffers = count > 1 ? std::min(2, std::max(1, c->blockBuffers)) : std::min(3, std::max(1, c->blockBuffers));
             planned.nBuffers = 1;
-            for (int nb = std::min(3, std::max(1, c->blockBuffers)); nb >= 1; --nb) {
+            for (int nb = wantBuffers; nb >= 1; --nb) {
                 if (blockPassSmemWs(planned.params.tileBits, nb, count, planned.maxUnits, tilesPerCta) <= kSmemBudget) {
                     planned.nBuffers = nb;
                     break;
                 }
             }
-            planned.smem = blockPassSmemWs(planned.params.tileBits, planned.nBuffers, count, planned.maxUnits, tilesPerCta);
+            size_t tableAt = blockPassTableArea(planned.params.tileBits, planned.nBuffers, count, planned.maxUnits, tilesPerCta);
+            const size_t tableBase = tableAt;
+            for (int i = 0; i < kPassMaxBlocks; ++i) planned.params.tableSmem[i] = kTableInGlobal;
+            if (count > 1 && c->blockTablesShared != 0) {
+                for (int i = 0; i < count; ++i) {
+                    const BlockDesc& b = planned.params.blocks[i];
+                    const size_t bytes = (static_cast<size_t>(16) << b.nCtx) << (2 * b.k);
+                    if (tableAt + bytes > kSmemBudget) continue;
+                    planned.params.tableSmem[i] = static_cast<uint32_t>(tableAt - tableBase);
+                    tableAt += bytes;
+                }
+            }
+            planned.smem = tableAt == tableBase ? blockPassSmemWs(planned.params.tileBits, planned.nBuffers, count, planned.maxUnits, tilesPerCta) : tableAt;
             if (planned.smem > kSmemBudget) return false;
             static bool wsAttr = false;
             if (!wsAttr) {
                 CUDA_TRY(cudaFuncSetAttribute(dmavm_block_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget)));
+                if (const char* carve = std::getenv("FLATDD_B200_CARVEOUT")) // experiments: shared-memory share of the L1 array in percent
+                    CUDA_TRY(cudaFuncSetAttribute(dmavm_block_ws_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(carve)));
                 wsAttr = true;
             }
             planned.warps = kComputeWarps + kMemoryWarps;
@@ -856,6 +875,7 @@ int fdd_set_option(fdd_ctx* ctx, const char* key, long value) {
         else if (k == "block_tile_bits") ctx->blockTileBits = static_cast<int>(value);
         else if (k == "block_max_per_pass") ctx->blockMaxPerPass = static_cast<int>(value);
         else if (k == "block_buffers") ctx->blockBuffers = static_cast<int>(value);
+        else if (k == "block_tables_shared") ctx->blockTablesShared = static_cast<int>(value);
         else if (k == "block_warps") ctx->blockWarps = static_cast<int>(value);
         else if (k == "block_units") ctx->blockUnits = static_cast<int>(value);
         else if (k == "block_ws") ctx->blockWs = static_cast<int>(value);
@@ -890,6 +910,7 @@ int fdd_get_option(const fdd_ctx* ctx, const char* key, long* value) {
         else if (k == "block_tile_bits") *value = ctx->blockTileBits;
         else if (k == "block_max_per_pass") *value = ctx->blockMaxPerPass;
         else if (k == "block_buffers") *value = ctx->blockBuffers;
+        else if (k == "block_tables_shared") *value = ctx->blockTablesShared;
         else if (k == "block_warps") *value = ctx->blockWarps;
         else if (k == "block_units") *value = ctx->blockUnits;
         else if (k == "block_ws") *value = ctx->blockWs;

@@ -212,6 +212,7 @@ bool planPass(const DenseBlock* const* blocks, int count, int nLocal, int rank, 
         return kLaneBits + __builtin_popcount(tileMask & ((1u << (q - kLaneBits)) - 1u));
     };
     std::memset(&pass, 0, sizeof pass);
+    for (uint32_t& off : pass.tableSmem) off = kTableInGlobal;
     pass.tileBits = tileBits;
     pass.nBlocks = count;
     pass.tileMask = tileMask;

@@ -171,6 +171,7 @@ template <int K, int WARPS, bool PREFETCH> struct BlockRunner {
     double aR[MT][KTL], aI[MT][KTL], aS[MT][KTL];
     uint32_t haveCtx;
     const double2* table;
+    uint32_t tableShared; // shared-memory address of the staged table, 0 when it is read from global memory
     int u0, u1;
 
     __device__ __forceinline__ void init(const BlockDesc& b, const uint32_t* __restrict__ laneTab, int warp, int lane) {
@@ -193,22 +194,43 @@ template <int K, int WARPS, bool PREFETCH> struct BlockRunner {
         }
         haveCtx = 0xffffffffu;
         table = reinterpret_cast<const double2*>(b.table);
-        // contiguous unit ranges per warp: the context bits vary slowest, so a warp rarely changes its matrix
-        const int perWarp = (b.nUnits + WARPS - 1) / WARPS;
-        u0 = warp * perWarp;
-        u1 = min(b.nUnits, u0 + perWarp);
+        tableShared = 0;
+        // contiguous unit ranges per warp (the context bits vary slowest, so a warp rarely changes its matrix), sizes differing
+        // by at most one
+        setRange(0, b.nUnits, warp, WARPS);
+    }
+    // this warp is member `member` of `members` warps that share the units [first, first + count)
+    __device__ __forceinline__ void setRange(int first, int count, int member, int members) {
+        const int base = count / members, rem = count % members;
+        u0 = first + member * base + min(member, rem);
+        u1 = u0 + base + (member < rem ? 1 : 0);
     }
 
     __device__ __forceinline__ void loadA(uint32_t ctx) {
-        const double2* m = table + static_cast<size_t>(ctx) * ROWS * ROWS;
+        if (tableShared != 0) {
+            const uint32_t m = tableShared + ctx * (ROWS * ROWS * 16u);
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
+            for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-            for (int kt = 0; kt < KTL; ++kt) {
-                const double2 w = __ldg(m + aAt[mt][kt]);
-                aR[mt][kt] = w.x;
-                aI[mt][kt] = w.y;
-                aS[mt][kt] = w.x + w.y;
+                for (int kt = 0; kt < KTL; ++kt) {
+                    double2 w;
+                    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];\n" : "=d"(w.x), "=d"(w.y) : "r"(m + 16u * static_cast<uint32_t>(aAt[mt][kt])));
+                    aR[mt][kt] = w.x;
+                    aI[mt][kt] = w.y;
+                    aS[mt][kt] = w.x + w.y;
+                }
+            }
+        } else {
+            const double2* m = table + static_cast<size_t>(ctx) * ROWS * ROWS;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                for (int kt = 0; kt < KTL; ++kt) {
+                    const double2 w = __ldg(m + aAt[mt][kt]);
+                    aR[mt][kt] = w.x;
+                    aI[mt][kt] = w.y;
+                    aS[mt][kt] = w.x + w.y;
+                }
             }
         }
         haveCtx = ctx;
@@ -241,6 +263,42 @@ template <int K, int WARPS, bool PREFETCH> struct BlockRunner {
     __device__ __forceinline__ void fetch(const double2* __restrict__ tile, uint32_t packed, double2 (&y)[KTL]) {
 #pragma unroll
         for (int kt = 0; kt < KTL; ++kt) y[kt] = tile[(packed & 0xffffu) ^ pBk[kt]];
+    }
+
+    // One unit after the other, only the B fragments of the next unit are fetched ahead: for CTAs with three compute warps per
+    // scheduler, where the other warps cover this warp's latencies and the registers do not allow two accumulator sets.
+    __device__ __forceinline__ void runLean(double2* __restrict__ tile, const uint32_t* __restrict__ unitTab, uint32_t ctxOut) {
+        if (u0 >= u1) return;
+        double2 yA[KTL], yB[KTL];
+        double a1[MT][2], a2[MT][2], a3[MT][2];
+        uint32_t pk = unitTab[u0];
+        fetch(tile, pk, yA);
+        for (int u = u0; u < u1; u += 2) {
+            uint32_t pkNext = 0;
+            if (u + 1 < u1) {
+                pkNext = unitTab[u + 1];
+                fetch(tile, pkNext, yB);
+            }
+            {
+                const uint32_t ctx = (pk >> 16) | ctxOut;
+                if (ctx != haveCtx) loadA(ctx);
+            }
+            issue(yA, a1, a2, a3);
+            finish(tile, pk & 0xffffu, a1, a2, a3);
+            if (u + 1 >= u1) break;
+            pk = pkNext;
+            if (u + 2 < u1) {
+                pkNext = unitTab[u + 2];
+                fetch(tile, pkNext, yA);
+            }
+            {
+                const uint32_t ctx = (pk >> 16) | ctxOut;
+                if (ctx != haveCtx) loadA(ctx);
+            }
+            issue(yB, a1, a2, a3);
+            finish(tile, pk & 0xffffu, a1, a2, a3);
+            pk = pkNext;
+        }
     }
 
     // Software pipeline over the warp's units, two accumulator sets: the tensor-core work of unit u + 1 is issued BEFORE the
@@ -315,20 +373,41 @@ __device__ __forceinline__ void mbarWait(uint64_t* bar, unsigned parity) {
         "}\n" ::"r"(addr), "r"(parity) : "memory");
 }
 
+// named barrier 2 + group for the 32 * members threads of a group of compute warps (ids are immediates: ptxas counts the barriers a kernel uses)
+template <int THREADS> __device__ __forceinline__ void groupBarrier(int group) {
+    switch (group) {
+    case 0: asm volatile("bar.sync 2, %0;\n" ::"n"(THREADS) : "memory"); break;
+    case 1: asm volatile("bar.sync 3, %0;\n" ::"n"(THREADS) : "memory"); break;
+    case 2: asm volatile("bar.sync 4, %0;\n" ::"n"(THREADS) : "memory"); break;
+    default: asm volatile("bar.sync 5, %0;\n" ::"n"(THREADS) : "memory"); break;
+    }
+}
+
 #ifndef FDD_BLOCK_COMPUTE_WARPS
 #define FDD_BLOCK_COMPUTE_WARPS 8
 #endif
 #ifndef FDD_BLOCK_PREFETCH
 #define FDD_BLOCK_PREFETCH 1
 #endif
-constexpr int kComputeWarps = FDD_BLOCK_COMPUTE_WARPS; // tensor-core warps of a CTA
+constexpr int kComputeWarps = FDD_BLOCK_COMPUTE_WARPS; // tensor-core warps of a CTA: 8 (two per scheduler, software-pipelined unit loop) or 12
 constexpr int kMemoryWarps = 4;  // warps that only move tiles between HBM and shared memory
 constexpr int kBlockThreads = 32 * (kComputeWarps + kMemoryWarps);
+static_assert(kComputeWarps == 8 || kComputeWarps == 12, "setmaxnreg works on groups of four warps; the unit split below knows 8 and 12");
+// Twelve compute warps: three per scheduler, each with the lean unit loop (152 registers).  They form four GROUPS of three
+// consecutive warps (which sit on three different schedulers); in a warp-local pass group g owns quarter g of the tile in every
+// block and only the three warps of a group wait for each other between blocks, so the groups drift apart and a scheduler
+// always has a warp with tensor work while another reloads its matrix or runs its epilogue.
+constexpr bool kLeanLoop = kComputeWarps == 12;
+constexpr int kGroupWarps = 3;
 
 // shared memory of the warp-specialised kernel: the tables as above, two mbarriers per buffer and the segment index of the
 // first segment of every tile this CTA will own (tilesPerCta words)
 __host__ __device__ inline size_t blockPassSmemWs(int tileBits, int nBuffers, int nBlocks, int maxUnits, uint32_t tilesPerCta) {
     return blockPassSmem(tileBits, nBuffers, nBlocks, maxUnits) + 16 * static_cast<size_t>(nBuffers) + 16 + 4 * static_cast<size_t>(tilesPerCta);
+}
+// the staged matrix tables follow, 16-byte aligned (PassParams::tableSmem holds offsets into this area)
+__host__ __device__ inline size_t blockPassTableArea(int tileBits, int nBuffers, int nBlocks, int maxUnits, uint32_t tilesPerCta) {
+    return (blockPassSmemWs(tileBits, nBuffers, nBlocks, maxUnits, tilesPerCta) + 15) & ~static_cast<size_t>(15);
 }
 
 // Warp-specialised pass.  Measured on B200: the copy-in / copy-out of a tile alone runs at 0.91 of the HBM copy peak, the
@@ -374,6 +453,16 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
     {
         uint32_t i = threadIdx.x;
         for (uint32_t t = blockIdx.x + i * gridDim.x; t < p.nTiles; t += blockDim.x * gridDim.x, i += blockDim.x) tileSeg[i] = spreadAround(t, p.tileMask);
+    }
+    // the matrix tables the pass keeps in shared memory
+    unsigned char* tableArea = smemRaw + blockPassTableArea(p.tileBits, nBuffers, p.nBlocks, maxUnits, (p.nTiles + gridDim.x - 1) / gridDim.x);
+    for (int g = 0; g < p.nBlocks; ++g) {
+        if (p.tableSmem[g] == kTableInGlobal) continue;
+        const BlockDesc& b = p.blocks[g];
+        const uint32_t n16 = (1u << b.nCtx) << (2 * b.k); // complex entries = 16-byte units
+        const double2* src = reinterpret_cast<const double2*>(b.table);
+        double2* dst = reinterpret_cast<double2*>(tableArea + p.tableSmem[g]);
+        for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     if (threadIdx.x == 0) {
         for (int b = 0; b < nBuffers; ++b) {
@@ -441,7 +530,8 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
         cp_async_wait<0>();
     } else {
         // =================== compute warps ==================================================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+        if (kLeanLoop) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;\n");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
         auto ctxOutOf = [&](const BlockDesc& b, uint32_t segBase) {
             uint32_t ctxOut = 0;
             for (int j = 0; j < b.nCtx; ++j) {
@@ -468,7 +558,10 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
                 const long long c0 = p.debugClocks != nullptr ? clock64() : 0;
                 mbarWait(full + buf, phase);
                 const long long c1 = p.debugClocks != nullptr ? clock64() : 0;
-                if (!(p.debugSkip & 1u)) runner.run(tile, unitTabs, ctxOut);
+                if (!(p.debugSkip & 1u)) {
+                    if (kLeanLoop) runner.runLean(tile, unitTabs, ctxOut);
+                    else runner.run(tile, unitTabs, ctxOut);
+                }
                 __syncwarp();
                 if (p.debugClocks != nullptr) {
                     cWait += c1 - c0;
@@ -504,20 +597,25 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
                 const BlockDesc& b = p.blocks[g];
                 const uint32_t ctxOut = ctxOutOf(b, segBase);
                 if (g > 0) {
-                    // the previous block has written what this one reads: this warp's own eighth of the tile when the pass is
-                    // warp local, else anywhere in the tile
-                    if (p.warpLocal) __syncwarp();
-                    else asm volatile("bar.sync 1, %0;\n" ::"n"(32 * kComputeWarps) : "memory");
+                    // the previous block has written what this one reads: this warp's own eighth (its group's quarter) of the tile
+                    // when the pass is warp local, else anywhere in the tile
+                    if (!p.warpLocal) asm volatile("bar.sync 1, %0;\n" ::"n"(32 * kComputeWarps) : "memory");
+                    else if (kLeanLoop) groupBarrier<32 * kGroupWarps>(warp / kGroupWarps);
+                    else __syncwarp();
                 }
-                if (b.k == 4) {
-                    BlockRunner<4, kComputeWarps, FDD_BLOCK_PREFETCH != 0> runner;
+                auto runBlock = [&](auto kTag) {
+                    BlockRunner<decltype(kTag)::value, kComputeWarps, FDD_BLOCK_PREFETCH != 0> runner;
                     runner.init(b, laneTabs + g * 32 * 8, warp, lane);
-                    runner.run(tile, unitTabs + g * maxUnits, ctxOut);
-                } else {
-                    BlockRunner<3, kComputeWarps, FDD_BLOCK_PREFETCH != 0> runner;
-                    runner.init(b, laneTabs + g * 32 * 8, warp, lane);
-                    runner.run(tile, unitTabs + g * maxUnits, ctxOut);
-                }
+                    if (p.tableSmem[g] != kTableInGlobal) runner.tableShared = static_cast<uint32_t>(__cvta_generic_to_shared(tableArea + p.tableSmem[g]));
+                    if (kLeanLoop) {
+                        if (p.warpLocal) runner.setRange((warp / kGroupWarps) * (b.nUnits >> 2), b.nUnits >> 2, warp % kGroupWarps, kGroupWarps);
+                        runner.runLean(tile, unitTabs + g * maxUnits, ctxOut);
+                    } else {
+                        runner.run(tile, unitTabs + g * maxUnits, ctxOut);
+                    }
+                };
+                if (b.k == 4) runBlock(std::integral_constant<int, 4>{});
+                else runBlock(std::integral_constant<int, 3>{});
             }
             __syncwarp();
             mbarArrive(done + buf); // release: this thread's writes to the tile are visible to the memory warps that wait

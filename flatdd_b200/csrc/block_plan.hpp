@@ -27,6 +27,7 @@ constexpr int kBlockMaxTargets = 4;   // k: dense qubits of one block (matrix 2^
 constexpr int kBlockMaxCtx = 10;      // context qubits of one block (2^ctx matrices)
 constexpr int kPassMaxBlocks = 6;     // blocks applied to a resident tile in one pass
 constexpr int kPassMaxTileBits = 13;  // 2^13 amplitudes = 128 KiB of shared memory
+constexpr uint32_t kTableInGlobal = 0xffffffffu;
 constexpr int kLaneBits = 5;          // the low 5 index bits always belong to the tile (512-byte runs in HBM)
 
 // ---- shared-memory layout of the tile ------------------------------------------------------------
@@ -95,6 +96,9 @@ struct PassParams {
     uint32_t warpLocal;     // 1: the top three unit bits of EVERY block are the same three tile bits, none of them a target of any block:
                             // compute warp w (of eight) touches the same eighth of the tile in every block, so the blocks of a pass need
                             // no barrier between them, only the warp's own order
+    uint32_t tableSmem[kPassMaxBlocks]; // byte offset of the block's matrix table in the CTA's shared-memory table area when the pass
+                            // stages it there (multi-block passes: every (tile, block) visit reloads the warp's A fragments, and from
+                            // global memory that is an L2 round trip under full HBM load), else kTableInGlobal
     uint32_t debugSkip;     // experiments (FLATDD_B200_BLOCK_SKIP): bit 0 = no tensor-core work, bit 1 = no global loads/stores
     long long* debugClocks; // experiments (FLATDD_B200_BLOCK_CLOCKS): per compute warp {cycles waiting for tiles, cycles in the blocks, total}
     BlockDesc blocks[kPassMaxBlocks];
