@@ -130,6 +130,7 @@ struct fdd_ctx {
                                // 2^13 fills the shared memory with one buffer: measured slower than separate passes)
     int blockWarps = 0;       // experiments: 16 = sixteen warps per CTA with one unit per iteration
     int blockUnits = 2;       // units per iteration and warp (2: twelve independent tensor-core chains, one CTA per SM; 1: two CTAs per SM)
+    int blockReorder = 1;      // blocks move up over gates they commute with to share a pass (orderForPasses)
     int blockTablesShared = 1; // multi-block passes keep the blocks' matrix tables in shared memory when they fit
     int blockBuffers = 3;     // tile buffers per CTA when they fit (copy-in, tensor-core work and copy-out of consecutive tiles overlap)
     int blockWs = 1;          // warp-specialised kernel (memory warps + compute warps); 0: every warp loads, computes and stores in turn
@@ -705,8 +706,71 @@ void walkWithTables(fdd_ctx* c, const fdd_gate* gate) {
     launchWalk(c, gate);
 }
 
+// A block may move up over gates it commutes with to share a pass with an earlier block: two blocks commute when neither
+// has a target among the other's targets or context qubits (a qubit both treat diagonally is harmless).  Greedy, in order:
+// the first gate not yet placed opens a pass; later blocks (within a window) join it while the pass still fits one tile and
+// they commute with every gate they jump over.  Gates that are not blocks are never crossed.  The product of the gates is
+// unchanged; only the order of commuting factors (and with it the last bits of the rounding) differs.
+std::vector<const fdd_gate*> orderForPasses(const fdd_ctx* c, const fdd_gate* const* gates, int count) {
+    std::vector<const fdd_gate*> out;
+    out.reserve(static_cast<size_t>(count));
+    const int cap = std::max(1, std::min(c->blockMaxPerPass, kPassMaxBlocks));
+    const int maxBits = std::min(c->nLocal, std::min(kPassMaxTileBits, c->blockMaxTileBits));
+    constexpr int kWindow = 48;
+    struct Masks {
+        uint64_t targets = 0, support = 0;
+        bool block = false;
+    };
+    std::vector<Masks> m(static_cast<size_t>(count));
+    for (int i = 0; i < count; ++i) {
+        if (!usesBlockPath(c, gates[i])) continue;
+        Masks& x = m[static_cast<size_t>(i)];
+        x.block = true;
+        for (int q : gates[i]->block->targets) x.targets |= uint64_t{1} << q;
+        x.support = x.targets;
+        for (int q : gates[i]->block->ctx) x.support |= uint64_t{1} << q;
+    }
+    std::vector<char> placed(static_cast<size_t>(count), 0);
+    for (int i = 0; i < count; ++i) {
+        if (placed[static_cast<size_t>(i)]) continue;
+        placed[static_cast<size_t>(i)] = 1;
+        out.push_back(gates[i]);
+        if (!m[static_cast<size_t>(i)].block || cap == 1) continue;
+        std::vector<const DenseBlock*> group{gates[i]->block.get()};
+        uint64_t skippedTargets = 0, skippedSupport = 0;
+        for (int j = i + 1; j < count && j <= i + kWindow && static_cast<int>(group.size()) < cap; ++j) {
+            if (placed[static_cast<size_t>(j)]) continue;
+            const Masks& x = m[static_cast<size_t>(j)];
+            if (!x.block) break;
+            bool joins = (x.targets & skippedSupport) == 0 && (x.support & skippedTargets) == 0;
+            if (joins) {
+                group.push_back(gates[j]->block.get());
+                const int need = minTileBits(group.data(), static_cast<int>(group.size()), c->nLocal);
+                if (need < 0 || need > maxBits) {
+                    group.pop_back();
+                    joins = false;
+                }
+            }
+            if (joins) {
+                placed[static_cast<size_t>(j)] = 1;
+                out.push_back(gates[j]);
+            } else {
+                skippedTargets |= x.targets;
+                skippedSupport |= x.support;
+            }
+        }
+    }
+    return out;
+}
+
 // gates[0..count) in order: consecutive blocks share a pass while they fit one tile, everything else takes the older kernels
-void applyGates(fdd_ctx* c, const fdd_gate* const* gates, int count, bool cachePlan) {
+void applyGates(fdd_ctx* c, const fdd_gate* const* gatesIn, int count, bool cachePlan) {
+    std::vector<const fdd_gate*> ordered;
+    const fdd_gate* const* gates = gatesIn;
+    if (c->blockReorder != 0 && count > 2) {
+        ordered = orderForPasses(c, gatesIn, count);
+        gates = ordered.data();
+    }
     int i = 0;
     while (i < count) {
         if (!usesBlockPath(c, gates[i])) {
@@ -876,6 +940,7 @@ int fdd_set_option(fdd_ctx* ctx, const char* key, long value) {
         else if (k == "block_max_per_pass") ctx->blockMaxPerPass = static_cast<int>(value);
         else if (k == "block_buffers") ctx->blockBuffers = static_cast<int>(value);
         else if (k == "block_tables_shared") ctx->blockTablesShared = static_cast<int>(value);
+        else if (k == "block_reorder") ctx->blockReorder = static_cast<int>(value);
         else if (k == "block_warps") ctx->blockWarps = static_cast<int>(value);
         else if (k == "block_units") ctx->blockUnits = static_cast<int>(value);
         else if (k == "block_ws") ctx->blockWs = static_cast<int>(value);
@@ -911,6 +976,7 @@ int fdd_get_option(const fdd_ctx* ctx, const char* key, long* value) {
         else if (k == "block_max_per_pass") *value = ctx->blockMaxPerPass;
         else if (k == "block_buffers") *value = ctx->blockBuffers;
         else if (k == "block_tables_shared") *value = ctx->blockTablesShared;
+        else if (k == "block_reorder") *value = ctx->blockReorder;
         else if (k == "block_warps") *value = ctx->blockWarps;
         else if (k == "block_units") *value = ctx->blockUnits;
         else if (k == "block_ws") *value = ctx->blockWs;

@@ -265,42 +265,6 @@ template <int K, int WARPS, bool PREFETCH> struct BlockRunner {
         for (int kt = 0; kt < KTL; ++kt) y[kt] = tile[(packed & 0xffffu) ^ pBk[kt]];
     }
 
-    // One unit after the other, only the B fragments of the next unit are fetched ahead: for CTAs with three compute warps per
-    // scheduler, where the other warps cover this warp's latencies and the registers do not allow two accumulator sets.
-    __device__ __forceinline__ void runLean(double2* __restrict__ tile, const uint32_t* __restrict__ unitTab, uint32_t ctxOut) {
-        if (u0 >= u1) return;
-        double2 yA[KTL], yB[KTL];
-        double a1[MT][2], a2[MT][2], a3[MT][2];
-        uint32_t pk = unitTab[u0];
-        fetch(tile, pk, yA);
-        for (int u = u0; u < u1; u += 2) {
-            uint32_t pkNext = 0;
-            if (u + 1 < u1) {
-                pkNext = unitTab[u + 1];
-                fetch(tile, pkNext, yB);
-            }
-            {
-                const uint32_t ctx = (pk >> 16) | ctxOut;
-                if (ctx != haveCtx) loadA(ctx);
-            }
-            issue(yA, a1, a2, a3);
-            finish(tile, pk & 0xffffu, a1, a2, a3);
-            if (u + 1 >= u1) break;
-            pk = pkNext;
-            if (u + 2 < u1) {
-                pkNext = unitTab[u + 2];
-                fetch(tile, pkNext, yA);
-            }
-            {
-                const uint32_t ctx = (pk >> 16) | ctxOut;
-                if (ctx != haveCtx) loadA(ctx);
-            }
-            issue(yB, a1, a2, a3);
-            finish(tile, pk & 0xffffu, a1, a2, a3);
-            pk = pkNext;
-        }
-    }
-
     // Software pipeline over the warp's units, two accumulator sets: the tensor-core work of unit u + 1 is issued BEFORE the
     // subtractions and stores of unit u, and the B fragments of unit u + 2 are fetched meanwhile — the tensor pipe's result
     // latency (about a hundred cycles) and the shared-memory latency are covered by the warp's own next unit instead of by
@@ -373,32 +337,16 @@ __device__ __forceinline__ void mbarWait(uint64_t* bar, unsigned parity) {
         "}\n" ::"r"(addr), "r"(parity) : "memory");
 }
 
-// named barrier 2 + group for the 32 * members threads of a group of compute warps (ids are immediates: ptxas counts the barriers a kernel uses)
-template <int THREADS> __device__ __forceinline__ void groupBarrier(int group) {
-    switch (group) {
-    case 0: asm volatile("bar.sync 2, %0;\n" ::"n"(THREADS) : "memory"); break;
-    case 1: asm volatile("bar.sync 3, %0;\n" ::"n"(THREADS) : "memory"); break;
-    case 2: asm volatile("bar.sync 4, %0;\n" ::"n"(THREADS) : "memory"); break;
-    default: asm volatile("bar.sync 5, %0;\n" ::"n"(THREADS) : "memory"); break;
-    }
-}
-
 #ifndef FDD_BLOCK_COMPUTE_WARPS
 #define FDD_BLOCK_COMPUTE_WARPS 8
 #endif
 #ifndef FDD_BLOCK_PREFETCH
 #define FDD_BLOCK_PREFETCH 1
 #endif
-constexpr int kComputeWarps = FDD_BLOCK_COMPUTE_WARPS; // tensor-core warps of a CTA: 8 (two per scheduler, software-pipelined unit loop) or 12
+constexpr int kComputeWarps = FDD_BLOCK_COMPUTE_WARPS; // tensor-core warps of a CTA (two per scheduler, software-pipelined unit loop)
 constexpr int kMemoryWarps = 4;  // warps that only move tiles between HBM and shared memory
 constexpr int kBlockThreads = 32 * (kComputeWarps + kMemoryWarps);
-static_assert(kComputeWarps == 8 || kComputeWarps == 12, "setmaxnreg works on groups of four warps; the unit split below knows 8 and 12");
-// Twelve compute warps: three per scheduler, each with the lean unit loop (152 registers).  They form four GROUPS of three
-// consecutive warps (which sit on three different schedulers); in a warp-local pass group g owns quarter g of the tile in every
-// block and only the three warps of a group wait for each other between blocks, so the groups drift apart and a scheduler
-// always has a warp with tensor work while another reloads its matrix or runs its epilogue.
-constexpr bool kLeanLoop = kComputeWarps == 12;
-constexpr int kGroupWarps = 3;
+static_assert(kComputeWarps == 8, "setmaxnreg works on groups of four warps; a warp-local pass gives each of eight warps an eighth of the tile");
 
 // shared memory of the warp-specialised kernel: the tables as above, two mbarriers per buffer and the segment index of the
 // first segment of every tile this CTA will own (tilesPerCta words)
@@ -530,8 +478,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
         cp_async_wait<0>();
     } else {
         // =================== compute warps ==================================================================
-        if (kLeanLoop) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;\n");
-        else asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
         auto ctxOutOf = [&](const BlockDesc& b, uint32_t segBase) {
             uint32_t ctxOut = 0;
             for (int j = 0; j < b.nCtx; ++j) {
@@ -558,10 +505,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
                 const long long c0 = p.debugClocks != nullptr ? clock64() : 0;
                 mbarWait(full + buf, phase);
                 const long long c1 = p.debugClocks != nullptr ? clock64() : 0;
-                if (!(p.debugSkip & 1u)) {
-                    if (kLeanLoop) runner.runLean(tile, unitTabs, ctxOut);
-                    else runner.run(tile, unitTabs, ctxOut);
-                }
+                if (!(p.debugSkip & 1u)) runner.run(tile, unitTabs, ctxOut);
                 __syncwarp();
                 if (p.debugClocks != nullptr) {
                     cWait += c1 - c0;
@@ -597,22 +541,16 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
                 const BlockDesc& b = p.blocks[g];
                 const uint32_t ctxOut = ctxOutOf(b, segBase);
                 if (g > 0) {
-                    // the previous block has written what this one reads: this warp's own eighth (its group's quarter) of the tile
-                    // when the pass is warp local, else anywhere in the tile
-                    if (!p.warpLocal) asm volatile("bar.sync 1, %0;\n" ::"n"(32 * kComputeWarps) : "memory");
-                    else if (kLeanLoop) groupBarrier<32 * kGroupWarps>(warp / kGroupWarps);
-                    else __syncwarp();
+                    // the previous block has written what this one reads: this warp's own eighth of the tile when the pass is
+                    // warp local, else anywhere in the tile
+                    if (p.warpLocal) __syncwarp();
+                    else asm volatile("bar.sync 1, %0;\n" ::"n"(32 * kComputeWarps) : "memory");
                 }
                 auto runBlock = [&](auto kTag) {
                     BlockRunner<decltype(kTag)::value, kComputeWarps, FDD_BLOCK_PREFETCH != 0> runner;
                     runner.init(b, laneTabs + g * 32 * 8, warp, lane);
                     if (p.tableSmem[g] != kTableInGlobal) runner.tableShared = static_cast<uint32_t>(__cvta_generic_to_shared(tableArea + p.tableSmem[g]));
-                    if (kLeanLoop) {
-                        if (p.warpLocal) runner.setRange((warp / kGroupWarps) * (b.nUnits >> 2), b.nUnits >> 2, warp % kGroupWarps, kGroupWarps);
-                        runner.runLean(tile, unitTabs + g * maxUnits, ctxOut);
-                    } else {
-                        runner.run(tile, unitTabs + g * maxUnits, ctxOut);
-                    }
+                    runner.run(tile, unitTabs + g * maxUnits, ctxOut);
                 };
                 if (b.k == 4) runBlock(std::integral_constant<int, 4>{});
                 else runBlock(std::integral_constant<int, 3>{});
