@@ -159,6 +159,11 @@ __device__ __forceinline__ void applyBlockToTile(const BlockDesc& b, double2* __
     }
 }
 
+// D = A B + C with D and C in different registers (a chain that branches off another chain's result needs no copy)
+__device__ __forceinline__ void dmma884From(double (&d)[2], double a, double b, const double (&c)[2]) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};\n" : "=d"(d[0]), "=d"(d[1]) : "d"(a), "d"(b), "d"(c[0]), "d"(c[1]));
+}
+
 // One block applied to resident tiles by a compute warp, with its constants (and, while the context does not change, its matrix
 // as A fragments) held in registers between calls: a pass of ONE block sets the runner up once per CTA instead of once per tile.
 // The B fragments of the next unit are fetched from shared memory before the tensor-core work of the current one.
@@ -168,7 +173,11 @@ template <int K, int WARPS, bool PREFETCH> struct BlockRunner {
     static constexpr int KTL = ROWS / 4;
     uint32_t pBk[KTL], pDm[MT], pK0;
     int aAt[MT][KTL];
-    double aR[MT][KTL], aI[MT][KTL], aS[MT][KTL];
+    // A fragments of the three real products of Z = M Y:  K1 = Mr (Yr + Yi),  Re Z = K1 - (Mr + Mi) Yi,  Im Z = K1 + (Mi - Mr) Yr.
+    // K1 is accumulated once (KTL DMMAs per M slab); the Re and Im chains both start from it (dmma884From) and end in the result:
+    // 3 KTL MT DMMAs per unit like any three-product form, but no subtraction afterwards — of the 16 additions per 16 x 16 unit
+    // (each waits for the FP64 pipe between the other warp's DMMAs) only the four Yr + Yi remain.
+    double aR[MT][KTL], aN[MT][KTL], aD[MT][KTL];
     uint32_t haveCtx;
     const double2* table;
     uint32_t tableShared; // shared-memory address of the staged table, 0 when it is read from global memory
@@ -216,8 +225,8 @@ template <int K, int WARPS, bool PREFETCH> struct BlockRunner {
                     double2 w;
                     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];\n" : "=d"(w.x), "=d"(w.y) : "r"(m + 16u * static_cast<uint32_t>(aAt[mt][kt])));
                     aR[mt][kt] = w.x;
-                    aI[mt][kt] = w.y;
-                    aS[mt][kt] = w.x + w.y;
+                    aN[mt][kt] = -w.x - w.y;
+                    aD[mt][kt] = w.y - w.x;
                 }
             }
         } else {
@@ -228,36 +237,46 @@ template <int K, int WARPS, bool PREFETCH> struct BlockRunner {
                 for (int kt = 0; kt < KTL; ++kt) {
                     const double2 w = __ldg(m + aAt[mt][kt]);
                     aR[mt][kt] = w.x;
-                    aI[mt][kt] = w.y;
-                    aS[mt][kt] = w.x + w.y;
+                    aN[mt][kt] = -w.x - w.y;
+                    aD[mt][kt] = w.y - w.x;
                 }
             }
         }
         haveCtx = ctx;
     }
 
-    // tensor-core work of one unit: accumulators <- M * y (three real products)
-    __device__ __forceinline__ void issue(const double2 (&y)[KTL], double (&p1)[MT][2], double (&p2)[MT][2], double (&p3)[MT][2]) {
+    // tensor-core work of one unit: zr, zi <- Re, Im of M * y
+    __device__ __forceinline__ void issue(const double2 (&y)[KTL], double (&zr)[MT][2], double (&zi)[MT][2]) {
+        double k1[MT][2];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) p1[mt][0] = p1[mt][1] = p2[mt][0] = p2[mt][1] = p3[mt][0] = p3[mt][1] = 0.0;
+        for (int mt = 0; mt < MT; ++mt) k1[mt][0] = k1[mt][1] = 0.0;
 #pragma unroll
         for (int kt = 0; kt < KTL; ++kt) {
             const double ys = y[kt].x + y[kt].y;
 #pragma unroll
+            for (int mt = 0; mt < MT; ++mt) dmma884(k1[mt], aR[mt][kt], ys);
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            dmma884From(zr[mt], aN[mt][0], y[0].y, k1[mt]);
+            dmma884From(zi[mt], aD[mt][0], y[0].x, k1[mt]);
+        }
+#pragma unroll
+        for (int kt = 1; kt < KTL; ++kt) {
+#pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-                dmma884(p1[mt], aR[mt][kt], y[kt].x);
-                dmma884(p2[mt], aI[mt][kt], y[kt].y);
-                dmma884(p3[mt], aS[mt][kt], ys);
+                dmma884(zr[mt], aN[mt][kt], y[kt].y);
+                dmma884(zi[mt], aD[mt][kt], y[kt].x);
             }
         }
     }
-    __device__ __forceinline__ void finish(double2* __restrict__ tile, uint32_t pu, const double (&p1)[MT][2], const double (&p2)[MT][2], const double (&p3)[MT][2]) {
+    __device__ __forceinline__ void finish(double2* __restrict__ tile, uint32_t pu, const double (&zr)[MT][2], const double (&zi)[MT][2]) {
         __syncwarp(); // in place: every lane holds this unit's inputs before any lane overwrites them
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
             const uint32_t at = pu ^ pDm[mt];
-            tile[at] = make_double2(p1[mt][0] - p2[mt][0], (p3[mt][0] - p1[mt][0]) - p2[mt][0]);
-            tile[at ^ pK0] = make_double2(p1[mt][1] - p2[mt][1], (p3[mt][1] - p1[mt][1]) - p2[mt][1]);
+            tile[at] = make_double2(zr[mt][0], zi[mt][0]);
+            tile[at ^ pK0] = make_double2(zr[mt][1], zi[mt][1]);
         }
     }
     __device__ __forceinline__ void fetch(const double2* __restrict__ tile, uint32_t packed, double2 (&y)[KTL]) {
@@ -272,7 +291,7 @@ template <int K, int WARPS, bool PREFETCH> struct BlockRunner {
     __device__ __forceinline__ void run(double2* __restrict__ tile, const uint32_t* __restrict__ unitTab, uint32_t ctxOut) {
         if (u0 >= u1) return;
         double2 yA[KTL], yB[KTL];
-        double a1[MT][2], a2[MT][2], a3[MT][2], b1[MT][2], b2[MT][2], b3[MT][2];
+        double aZr[MT][2], aZi[MT][2], bZr[MT][2], bZi[MT][2];
         uint32_t pkA = unitTab[u0], pkB = 0;
         fetch(tile, pkA, yA);
         if (u0 + 1 < u1) {
@@ -283,32 +302,32 @@ template <int K, int WARPS, bool PREFETCH> struct BlockRunner {
             const uint32_t ctx = (pkA >> 16) | ctxOut;
             if (ctx != haveCtx) loadA(ctx);
         }
-        issue(yA, a1, a2, a3);
+        issue(yA, aZr, aZi);
         for (int u = u0; u < u1; u += 2) {
             // accumulators A hold unit u in flight; yB holds the inputs of unit u + 1
             const uint32_t puA = pkA & 0xffffu;
             if (u + 1 < u1) {
                 const uint32_t ctx = (pkB >> 16) | ctxOut;
                 if (ctx != haveCtx) loadA(ctx);
-                issue(yB, b1, b2, b3);
+                issue(yB, bZr, bZi);
             }
             if (u + 2 < u1) {
                 pkA = unitTab[u + 2];
                 fetch(tile, pkA, yA);
             }
-            finish(tile, puA, a1, a2, a3);
+            finish(tile, puA, aZr, aZi);
             if (u + 1 >= u1) break;
             const uint32_t puB = pkB & 0xffffu;
             if (u + 2 < u1) {
                 const uint32_t ctx = (pkA >> 16) | ctxOut;
                 if (ctx != haveCtx) loadA(ctx);
-                issue(yA, a1, a2, a3);
+                issue(yA, aZr, aZi);
             }
             if (u + 3 < u1) {
                 pkB = unitTab[u + 3];
                 fetch(tile, pkB, yB);
             }
-            finish(tile, puB, b1, b2, b3);
+            finish(tile, puB, bZr, bZi);
         }
     }
 };
