@@ -217,13 +217,13 @@ template <int K, int WARPS, bool PREFETCH> struct BlockRunner {
 
     __device__ __forceinline__ void loadA(uint32_t ctx) {
         if (tableShared != 0) {
-            const uint32_t m = tableShared + ctx * (ROWS * ROWS * 16u);
+            const uint32_t m = tableShared + ctx * (ROWS * ROWS * 16u); // tableShared already points at this lane's column of the fragment rows
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
                 for (int kt = 0; kt < KTL; ++kt) {
                     double2 w;
-                    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];\n" : "=d"(w.x), "=d"(w.y) : "r"(m + 16u * static_cast<uint32_t>(aAt[mt][kt])));
+                    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];\n" : "=d"(w.x), "=d"(w.y) : "r"(m + 512u * static_cast<uint32_t>(mt * KTL + kt)));
                     aR[mt][kt] = w.x;
                     aN[mt][kt] = -w.x - w.y;
                     aD[mt][kt] = w.y - w.x;
@@ -421,20 +421,32 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
         uint32_t i = threadIdx.x;
         for (uint32_t t = blockIdx.x + i * gridDim.x; t < p.nTiles; t += blockDim.x * gridDim.x, i += blockDim.x) tileSeg[i] = spreadAround(t, p.tileMask);
     }
-    // the matrix tables the pass keeps in shared memory
     unsigned char* tableArea = smemRaw + blockPassTableArea(p.tileBits, nBuffers, p.nBlocks, maxUnits, (p.nTiles + gridDim.x - 1) / gridDim.x);
-    for (int g = 0; g < p.nBlocks; ++g) {
-        if (p.tableSmem[g] == kTableInGlobal) continue;
-        const BlockDesc& b = p.blocks[g];
-        const uint32_t n16 = (1u << b.nCtx) << (2 * b.k); // complex entries = 16-byte units
-        const double2* src = reinterpret_cast<const double2*>(b.table);
-        double2* dst = reinterpret_cast<double2*>(tableArea + p.tableSmem[g]);
-        for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
-    }
     if (threadIdx.x == 0) {
         for (int b = 0; b < nBuffers; ++b) {
             mbarInit(full + b, 32 * kMemoryWarps);
             mbarInit(done + b, 32 * kComputeWarps); // every compute thread arrives: each one releases its own writes to the tile
+        }
+    }
+    __syncthreads();
+    // the matrix tables the pass keeps in shared memory, in A-FRAGMENT order: entry ((matrix * MT + mt) * KTL + kt) * 32 + lane is the
+    // element lane `lane` feeds to the DMMAs of slab (mt, kt) (laneTabs words 4..7), so a warp reads a matrix as MT KTL
+    // contiguous 512-byte rows without a bank conflict (in matrix order the eight rows of a fragment share their banks)
+    for (int g = 0; g < p.nBlocks; ++g) {
+        if (p.tableSmem[g] == kTableInGlobal) continue;
+        const BlockDesc& b = p.blocks[g];
+        const uint32_t perMatrix = 1u << (2 * b.k); // complex entries of a matrix = fragment slots (every entry belongs to one lane and slab)
+        const int ktl = b.k == 4 ? 4 : 2;
+        const uint32_t total = perMatrix << b.nCtx;
+        const double2* src = reinterpret_cast<const double2*>(b.table);
+        double2* dst = reinterpret_cast<double2*>(tableArea + p.tableSmem[g]);
+        const uint32_t* lt = laneTabs + g * 32 * 8;
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+            const uint32_t slot = i & (perMatrix - 1u);
+            const uint32_t ln = slot & 31u, frag = slot >> 5; // frag = mt * KTL + kt
+            const uint32_t mt = frag / static_cast<uint32_t>(ktl), kt = frag % static_cast<uint32_t>(ktl);
+            const uint32_t at = (lt[ln * 8 + 4 + 2 * mt + (kt >> 1)] >> (16 * (kt & 1))) & 0xffffu;
+            dst[i] = __ldg(src + (i - slot) + at);
         }
     }
     __syncthreads();
@@ -568,7 +580,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
                 auto runBlock = [&](auto kTag) {
                     BlockRunner<decltype(kTag)::value, kComputeWarps, FDD_BLOCK_PREFETCH != 0> runner;
                     runner.init(b, laneTabs + g * 32 * 8, warp, lane);
-                    if (p.tableSmem[g] != kTableInGlobal) runner.tableShared = static_cast<uint32_t>(__cvta_generic_to_shared(tableArea + p.tableSmem[g]));
+                    if (p.tableSmem[g] != kTableInGlobal) runner.tableShared = static_cast<uint32_t>(__cvta_generic_to_shared(tableArea + p.tableSmem[g])) + 16u * static_cast<uint32_t>(lane);
                     runner.run(tile, unitTabs + g * maxUnits, ctxOut);
                 };
                 if (b.k == 4) runBlock(std::integral_constant<int, 4>{});
