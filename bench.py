@@ -11,7 +11,7 @@ bench_inputs/traces/); nothing here reads /root/reference.
 
 Metric: array-phase circuit operations per second ("gates/s"); seconds per circuit is echoed.
   value  kernels only, gate tables resident in HBM (compiled once), CUDA events on the library stream
-  e2e    the same step through the host-buffer C-ABI: fdd_convert + fdd_apply per gate (gate
+  e2e    the same step through the host-buffer C-ABI: fdd_convert + fdd_apply_many per schedule stretch (gate
          compilation and table upload inside) + fdd_get_state into pinned host memory
   roofline  dmavm_tile_kernel: 32 * 2^n algorithmic bytes per launch / mean launch time vs the
          measured HBM copy bandwidth in MEASURED_PEAKS.json
@@ -336,14 +336,23 @@ def measure(workload: str, args, steps: int, warmup: int, with_e2e: bool) -> dic
         d2h = 16 * download
 
         def step_e2e():
+            # the calls the drop-in driver makes (GpuSwitchSimulator::runSchedule): the host tables of a schedule stretch cross
+            # the boundary in one fdd_apply_many call, so its dense blocks share passes exactly as in the device-timed step
             ctx.convert(vec)
+            stretch = []
             for r in records[1:]:
                 if r.kind == 2:
-                    ctx.apply(r.dd)
-                elif r.kind == 3:
+                    stretch.append(r.dd)
+                    continue
+                if stretch:
+                    ctx.apply_many(stretch)
+                    stretch = []
+                if r.kind == 3:
                     ctx.exchange_qubits(r.exchange[0], r.exchange[1], method)
                 else:
                     ctx.relabel_qubits(*r.exchange)
+            if stretch:
+                ctx.apply_many(stretch)
             if world > 1:
                 ctx.canonicalize()  # what getVector does for a sharded state: rank r = amplitudes with top index bits r
             if download == local_dim:
@@ -415,7 +424,9 @@ def measure(workload: str, args, steps: int, warmup: int, with_e2e: bool) -> dic
         table = json.loads(tf.read_text())
         traffic = (table["dmavm_block_ws_kernel"]["dram_bytes_per_launch"] * block_passes +
                    table["dmavm_tile_kernel"]["dram_bytes_per_launch"] * other_launches) / passes
-    tensor_peak = 44.2  # TFLOP/s, DMMA.8x8x4 alone on this pool's B200 (tools/dmma_probe.cu, profiles/r02_dmma_probe.jsonl)
+    # TFLOP/s of DMMA.8x8x4 alone on this pool's B200: one DMMA (512 flop) per 16.1-16.4 cycles and scheduler at 1965 MHz
+    # (tools/dmma_chain_probe.cu, tools/dadd_probe.cu: 37.0; ncu sm__ops_path_tensor_src_fp64 peak_sustained 128 flop/cycle/SM: 37.2)
+    tensor_peak = 37.2
     res = {
         "workload": workload, "n_qubits": n, "n_gates": n_gates, "n_exch": n_exch, "array_ops": array_ops, "n_local": n_local,
         "value": array_ops / (t_step_ms * 1e-3), "ms_per_step": t_step_ms, "convert_ms": statistics.mean(convert_ms),
@@ -429,7 +440,7 @@ def measure(workload: str, args, steps: int, warmup: int, with_e2e: bool) -> dic
                      "dram_gbs": dram_gbs, "dram_frac": dram_gbs / peak, "dram_bytes_per_launch": 32 * local_dim,
                      "tensor": {"pipe": "FP64 DMMA.8x8x4", "tflops": block_flops / (dmavm_ms * 1e-3) / 1e12, "peak_tflops": tensor_peak,
                                 "frac": block_flops / (dmavm_ms * 1e-3) / 1e12 / tensor_peak,
-                                "peak_source": "measured: DMMA alone, tools/dmma_probe.cu (44.2 TFLOP/s; 31-32 with the loop's shared-memory traffic and additions)"},
+                                "peak_source": "measured: DMMA alone, tools/dmma_chain_probe.cu and tools/dadd_probe.cu (37.0 TFLOP/s = one DMMA per 16.1 cycles and scheduler; ncu's peak_sustained for the pipe: 37.2)"},
                      "convert_gbs": 16.0 * local_dim / (statistics.mean(convert_ms) * 1e-3) / 1e9},
         "check": {"norm2_device": norm2, "max_amp_err_vs_reference": amp_err, "reference_samples_checked": n_checked,
                   "reference": "unmodified reference FlatDD (oracle/ref_dump), sampled amplitudes in bench_inputs/samples/"

@@ -5,6 +5,9 @@
 #include "kernels.cuh"
 #include "comm.cuh"
 #include "block_compile.hpp"
+#include <atomic>
+#include <exception>
+#include <thread>
 #include "block_kernel.cuh"
 
 #include <algorithm>
@@ -529,22 +532,32 @@ void freeGate(fdd_gate* g, cudaStream_t stream) {
 // ---- dense-block path -------------------------------------------------------------------------------------------
 // The gate as a dense block, padded to the kernel's shapes, with its table on the device; leaves g->block empty when the
 // gate is not a block (more than four non-diagonal qubits, too many context qubits, a non-local target, a tiny register).
-void attachBlock(fdd_ctx* c, fdd_gate* g, const fdd_matdd& dd) {
-    if (!c->blockKernel || c->variant != 2 || c->nLocal < 8) return;
+// The gate as a dense block, or nothing when it is not one.  Host work only (no CUDA call, touches nothing but `dd`): runs on
+// several threads when a boundary call brings many gates.
+std::unique_ptr<DenseBlock> extractBlock(const fdd_ctx* c, const fdd_matdd& dd) {
+    if (!c->blockKernel || c->variant != 2 || c->nLocal < 8) return nullptr;
     auto blk = std::make_unique<DenseBlock>();
-    if (!denseBlockFromDD(dd, *blk)) return;
+    if (!denseBlockFromDD(dd, *blk)) return nullptr;
     for (int q : blk->targets) {
-        if (q >= c->nLocal) return; // non-diagonal on a global qubit: the caller has to exchange first (launchWalk reports it)
+        if (q >= c->nLocal) return nullptr; // non-diagonal on a global qubit: the caller has to exchange first (launchWalk reports it)
     }
     padBlock(*blk, c->nLocal);
     const DenseBlock* one = blk.get();
-    if (minTileBits(&one, 1, c->nLocal) < 0) return;
+    if (minTileBits(&one, 1, c->nLocal) < 0) return nullptr;
+    return blk;
+}
+
+// The block's matrix table goes to the device (stream ordered).
+void uploadBlock(fdd_ctx* c, fdd_gate* g, std::unique_ptr<DenseBlock> blk) {
+    if (!blk) return;
     const size_t bytes = blk->table.size() * sizeof(double);
     CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&g->dTable), bytes, c->stream));
     CUDA_TRY(cudaMemcpyAsync(g->dTable, blk->table.data(), bytes, cudaMemcpyHostToDevice, c->stream)); // pageable: staged before the call returns
     g->block = std::move(blk);
     g->serial = ++c->gateSerial;
 }
+
+void attachBlock(fdd_ctx* c, fdd_gate* g, const fdd_matdd& dd) { uploadBlock(c, g, extractBlock(c, dd)); }
 
 // (dmavm_variant != 2 asks for one of the older kernels explicitly)
 bool usesBlockPath(const fdd_ctx* c, const fdd_gate* g) { return c->blockKernel && c->variant == 2 && g->block != nullptr && g->dTable != nullptr; }
@@ -1308,13 +1321,38 @@ int fdd_apply_many(fdd_ctx* ctx, const fdd_matdd* gates, int count) {
         };
         try {
             for (int i = 0; i < count; ++i) {
-                const fdd_matdd& dd = gates[i];
-                if (dd.n_qubits != ctx->n) throw std::invalid_argument("gate has " + std::to_string(dd.n_qubits) + " qubits, context has " + std::to_string(ctx->n));
+                if (gates[i].n_qubits != ctx->n) throw std::invalid_argument("gate has " + std::to_string(gates[i].n_qubits) + " qubits, context has " + std::to_string(ctx->n));
+            }
+            // the DD -> block expansion of every gate is host work (a quarter of a millisecond per fused gate of supremacy_n26):
+            // on a few threads, so that the device does not wait for it
+            std::vector<std::unique_ptr<DenseBlock>> blocks(static_cast<size_t>(count));
+            const int nThreads = std::max(1, std::min({count / 4, 8, static_cast<int>(std::thread::hardware_concurrency())}));
+            if (nThreads > 1) {
+                std::vector<std::thread> pool;
+                std::vector<std::exception_ptr> errors(static_cast<size_t>(nThreads));
+                std::atomic<int> next{0};
+                for (int t = 0; t < nThreads; ++t) {
+                    pool.emplace_back([&, t] {
+                        try {
+                            for (int i = next.fetch_add(1); i < count; i = next.fetch_add(1)) blocks[static_cast<size_t>(i)] = extractBlock(ctx, gates[i]);
+                        } catch (...) {
+                            errors[static_cast<size_t>(t)] = std::current_exception();
+                        }
+                    });
+                }
+                for (auto& th : pool) th.join();
+                for (auto& e : errors) {
+                    if (e) std::rethrow_exception(e);
+                }
+            } else {
+                for (int i = 0; i < count; ++i) blocks[static_cast<size_t>(i)] = extractBlock(ctx, gates[i]);
+            }
+            for (int i = 0; i < count; ++i) {
                 auto g = new fdd_gate();
                 owned.push_back(g);
                 g->device = ctx->device;
-                g->source = &dd; // the older kernels' tables are only made if a launch needs them
-                attachBlock(ctx, g, dd);
+                g->source = &gates[i]; // the older kernels' tables are only made if a launch needs them
+                uploadBlock(ctx, g, std::move(blocks[static_cast<size_t>(i)]));
             }
             applyGates(ctx, owned.data(), count, false);
         } catch (...) {

@@ -16,6 +16,7 @@
 // three real products per complex product) where a fused block is a real dense contraction on 3 or 4
 // upper qubits (tolerance 1e-10, measured <= 1e-13 against the reference; see DESIGN.md sections 3.2, 5).
 #pragma once
+#include <climits>
 
 #include "gate_compile.hpp"
 
@@ -115,6 +116,26 @@ struct ConvertParams {
     double2* out;
 };
 
+// One value of the expansion of a segment's sub-DD: the product so far, the node it has reached, "a zero weight was met".
+constexpr int kConvertZero = INT_MIN; // ConvertPath::node of a path that has met a zero weight
+struct ConvertPath {
+    double2 a;
+    int node; // the node reached, or kConvertZero (one shuffle carries both facts)
+};
+// One step down the DD for every lane: the parent's value comes from lane `src`, the edge taken is `bit`.
+__device__ __forceinline__ ConvertPath convertStep(const VecNode* __restrict__ nodes, const ConvertPath& parent, int src, int bit) {
+    ConvertPath r;
+    r.a = shfl2(parent.a, src);
+    r.node = __shfl_sync(0xffffffffu, parent.node, src);
+    if (r.node != kConvertZero) {
+        const VecNode& nd = nodes[r.node];
+        const double2 w = nd.w[bit];
+        r.a = cmul_exact(r.a, w);
+        r.node = (w.x == 0.0 && w.y == 0.0) ? kConvertZero : nd.child[bit];
+    }
+    return r;
+}
+
 // amplitude(i) = w_root * prod_v w(node_v.e[bit_v(i)]), multiplied root first, leaf last
 // (reference getValueByPathPar, include/dd/SwitchPackage.hpp:3605-3634).
 __global__ void __launch_bounds__(256) convert_kernel(const ConvertParams p) {
@@ -164,10 +185,47 @@ __global__ void __launch_bounds__(256) convert_kernel(const ConvertParams p) {
                 dead = (w.x == 0.0 && w.y == 0.0);
             }
         }
-        // ---- phase B: sweep the segments, lane = amplitude -------------------------------------
+        const int nSegTile = min(32u, p.nSeg - tile * 32u);
+        // ---- phase B, full tiles of 32-amplitude segments: the sub-DD below every segment is expanded as a TREE ----------
+        // The 32 amplitudes of a segment share their partial products: 2 distinct values after level 4, 4 after level 3, ...
+        // Step m (m = 1..5 bits decided) works on 32 >> m segments at once, lane = (segment slot << m) | (decided bits,
+        // level 4 first), and takes its parent from the step above by shuffle; depth first, sixteen segments per round:
+        // 1 + 2 + 4 + 8 + 16 = 31 steps for 16 segments instead of 5 per segment (2.6 times fewer table look-ups and
+        // multiplications; the kernel was bound by the shared-memory look-ups).  Every amplitude is still
+        // ((((c w4) w3) w2) w1) w0 with the same un-fused arithmetic: bit-identical to the reference.  After step 5 the lane
+        // index is the amplitude index inside the segment: 512-byte coalesced stores.
+        if (S == 5 && nSegTile == 32) {
+            ConvertPath top;
+            top.a = c;
+            top.node = dead ? kConvertZero : node;
+            double2* outTile = p.out + (static_cast<uint64_t>(tile) << 10);
+#pragma unroll 1
+            for (int round = 0; round < 2; ++round) {
+                const ConvertPath s1 = convertStep(nodes, top, 16 * round + (lane >> 1), lane & 1);
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const ConvertPath s2 = convertStep(nodes, s1, ((h2 * 8 + (lane >> 2)) << 1) | ((lane & 3) >> 1), lane & 1);
+#pragma unroll
+                    for (int h3 = 0; h3 < 2; ++h3) {
+                        const ConvertPath s3 = convertStep(nodes, s2, ((h3 * 4 + (lane >> 3)) << 2) | ((lane & 7) >> 1), lane & 1);
+#pragma unroll
+                        for (int h4 = 0; h4 < 2; ++h4) {
+                            const ConvertPath s4 = convertStep(nodes, s3, ((h4 * 2 + (lane >> 4)) << 3) | ((lane & 15) >> 1), lane & 1);
+#pragma unroll
+                            for (int h5 = 0; h5 < 2; ++h5) {
+                                const ConvertPath s5 = convertStep(nodes, s4, (h5 << 4) | (lane >> 1), lane & 1);
+                                const int seg16 = h2 * 8 + h3 * 4 + h4 * 2 + h5;
+                                st_stream(outTile + ((16 * round + seg16) << 5) + lane, s5.node == kConvertZero ? make_double2(0.0, 0.0) : s5.a);
+                            }
+                        }
+                    }
+                }
+            }
+            continue;
+        }
+        // ---- phase B, ragged tiles and short segments: sweep the segments, lane = amplitude ------------------------------
         // four segments at a time: four independent multiply chains per lane hide the latency of the
         // dependent table look-ups (the arithmetic of every chain is unchanged)
-        const int nSegTile = min(32u, p.nSeg - tile * 32u);
         constexpr int U = 4;
         for (int j0 = 0; j0 < nSegTile; j0 += U) {
             double2 a[U];

@@ -84,6 +84,70 @@ def test_blocks_share_a_pass(sets, passes):
     assert G.max_amp_err(re, im, sre, sim) < 1e-14
 
 
+def test_commuting_blocks_move_up_to_share_a_pass():
+    """orderForPasses (api.cu): A, B, A', B' with A and B on disjoint upper qubits (eight between them: no common tile) run as the
+    passes [A, A'] and [B, B'] because A' commutes with B; without the reordering every block has its own pass."""
+    n = 15
+    rng = np.random.default_rng(11)
+    sets = ([5, 6, 7, 8], [9, 10, 11, 12], [8, 7, 6, 5], [12, 9, 10, 11])
+    gates = [B.gate_dd(n, s, B.random_unitary(len(s), rng)) for s in sets]
+    yr, yi = B.random_state(n, rng)
+    wr, wi = yr, yi
+    for g in gates:
+        wr, wi = pyoracle.dmavm(g, wr, wi)
+    re, im, stats = apply_all(n, gates, yr, yi, many=True)
+    assert stats["blocks_applied"] == 4 and stats["block_launches"] == 2
+    assert G.max_amp_err(re, im, wr, wi) < AMP_TOL
+    ore, oim, plain = apply_all(n, gates, yr, yi, [("block_reorder", 0)], many=True)
+    assert plain["block_launches"] == 4
+    assert G.max_amp_err(ore, oim, wr, wi) < AMP_TOL
+
+
+def test_blocks_that_do_not_commute_keep_their_order():
+    """C shares qubit 12 with B, so it may not jump over B to join A's pass; a control qubit shared by two gates does not stop them
+    (both are diagonal in it), a control that is another gate's target does."""
+    n = 15
+    rng = np.random.default_rng(12)
+    a = B.gate_dd(n, [5, 6, 7, 8], B.random_unitary(4, rng))
+    b = B.gate_dd(n, [9, 10, 11, 12], B.random_unitary(4, rng))
+    c = B.gate_dd(n, [5, 6, 7, 12], B.random_unitary(4, rng))
+    d = B.gate_dd(n, [3, 13, 14], B.controlled(B.random_unitary(2, rng), 1))   # control 3
+    e = B.gate_dd(n, [3, 5, 6], B.controlled(B.random_unitary(2, rng), 1))     # control 3 as well: commutes with d
+    f = B.gate_dd(n, [3, 4], B.random_unitary(2, rng))                         # target 3: commutes with neither
+    for gates in ([a, b, c], [d, b, e], [d, f, e], [a, d, b, f, c, e]):
+        yr, yi = B.random_state(n, rng)
+        wr, wi = yr, yi
+        for g in gates:
+            wr, wi = pyoracle.dmavm(g, wr, wi)
+        re, im, _ = apply_all(n, gates, yr, yi, many=True)
+        assert G.max_amp_err(re, im, wr, wi) < AMP_TOL
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_block_sequences_reordered_vs_oracle(seed):
+    n = 15
+    rng = np.random.default_rng(100 + seed)
+    gates = []
+    for _ in range(12):
+        k = int(rng.integers(1, 5))
+        qubits = [int(q) for q in rng.choice(n, size=k + int(rng.integers(0, 3)), replace=False)]
+        controls, targets = qubits[k:], qubits[:k]
+        u = B.random_unitary(k, rng)
+        gates.append(B.gate_dd(n, controls + targets, B.controlled(u, len(controls)) if controls else u))
+    yr, yi = B.random_state(n, rng)
+    wr, wi = yr, yi
+    for g in gates:
+        wr, wi = pyoracle.dmavm(g, wr, wi)
+    re, im, stats = apply_all(n, gates, yr, yi, many=True)
+    assert G.max_amp_err(re, im, wr, wi) < AMP_TOL
+    ore, oim, plain = apply_all(n, gates, yr, yi, [("block_reorder", 0)], many=True)
+    assert G.max_amp_err(ore, oim, wr, wi) < AMP_TOL
+    assert stats["block_launches"] <= plain["block_launches"]
+    # the matrix tables of a shared pass from global memory instead of shared memory: the same arithmetic
+    gre, gim, _ = apply_all(n, gates, yr, yi, [("block_tables_shared", 0)], many=True)
+    assert G.max_amp_err(gre, gim, re, im) == 0.0
+
+
 def test_wide_gate_falls_back_to_the_older_kernels():
     n = 14
     rng = np.random.default_rng(3)
