@@ -96,10 +96,14 @@ int fdd_n_qubits(const fdd_ctx* ctx);
 int fdd_n_local_qubits(const fdd_ctx* ctx);
 int fdd_synchronize(fdd_ctx* ctx);
 /* Tunables for experiments: "dmavm_variant" (2 tile kernel where the gate allows, 1 / 0 walk kernels, 9 chunk kernel),
- * "warps_per_cta", "ctas_per_sm", "prefetch", "tile_mode", "dense_slots", "dmma", "flat_table", "pdl", "context_table", "exchange_unroll", "exchange_ctas_per_sm". */
+ * "warps_per_cta", "ctas_per_sm", "prefetch", "tile_mode", "dense_slots", "dmma", "flat_table", "pdl", "context_table", "exchange_unroll", "exchange_ctas_per_sm";
+ * the dense-block path: "block_kernel" (0: older kernels only), "block_tile_bits", "block_max_tile_bits", "block_max_per_pass" (blocks that may share a pass),
+ * "block_buffers", "block_ws", "block_tables_shared" (matrix tables of a shared pass in shared memory), "block_reorder" (blocks move up over gates they
+ * commute with to share a pass; 0 keeps the caller's order). */
 int fdd_set_option(fdd_ctx* ctx, const char* key, long value);
 /* Reads a tunable back, or a launch counter: "launches", "tensor_core_launches" (DMAVM launches that ran the
- * FP64 tensor-core path), "flat_table_launches", "context_table_launches", "exchanges". */
+ * FP64 tensor-core path), "flat_table_launches", "context_table_launches", "exchanges", "block_launches" (passes of the dense-block
+ * kernel), "blocks_applied" (fused gates those passes applied). */
 int fdd_get_option(const fdd_ctx* ctx, const char* key, long* value);
 
 /* ---- multi-GPU (one process per GPU) ----------------------------------
@@ -145,7 +149,9 @@ int fdd_apply(fdd_ctx* ctx, const fdd_matdd* gate);
  * call).  Handing the library the whole stretch lets it keep the state tile-resident across gates: consecutive gates that are
  * dense blocks (at most four non-diagonal qubits, at most ten qubits they depend on diagonally) are applied in ONE pass over
  * the state while their target qubits fit one shared-memory tile — 32 bytes of HBM traffic per amplitude for the group
- * instead of per gate. */
+ * instead of per gate.  A block may be applied earlier than its place in the list when it commutes with every gate it
+ * passes (no target of one among the targets or context qubits of the other), so that it can share a pass: the product of
+ * the gates is the same, the order of commuting factors is not ("block_reorder" = 0 keeps the list order). */
 int fdd_apply_many(fdd_ctx* ctx, const fdd_matdd* gates, int count);
 /* Host only, no device needed: the gate as a DENSE BLOCK (north_star: "gate DDs are flattened to dense 2^k x 2^k blocks for
  * the fused qubit set") — `targets`: its non-diagonal qubits (ascending, at most 4), `controls`: the other qubits its matrix
