@@ -3,10 +3,11 @@
 // flat gate-DD builder (flatdd_b200/host/standalone.hpp).  The state
 // starts flat on the device, every (fused) gate is a DMAVM launch through the C-ABI.
 //
-//   flatdd_gpu_standalone --file C.qasm [--fuse 0|1|2] [--max-block 5] [--max-nondiag 4] [--gpu D]
+//   flatdd_gpu_standalone --file C.qasm [--fuse 0|1|2|3] [--max-block 5] [--max-nondiag 4] [--gpu D]
 //                         [--bin FILE] [--pv] [--shots N --seed S] [--time-gates] [--quiet]
 //                         [--trace FILE [--trace-only]] [--load STATE.bin] [--world N (with --trace-only: schedule for N shards)]
 // --fuse 0: one launch per gate; 1: dense-block fusion with commuting open blocks; 2: dependency-graph dense-block fusion
+//         (dense matrices, GPU cost model); 3: dependency-graph fusion on block tables (<= 4 non-diagonal + <= 5 context qubits)
 // (fewest launches).  Flags of the reference that only steer its DD phase (-t, --thresh, --beta, --no_cache, --DDSIM_convert,
 // --ps) are accepted and ignored.  --load resumes from a state written by --bin (checkpoint / resume).
 // --trace-only records the boundary traffic without touching a GPU
@@ -73,7 +74,7 @@ int main(int argc, char** argv) {
         return 1;
     }
     if (args.has("help") || args.has("h") || !args.has("file")) {
-        std::cout << "usage: flatdd_gpu_standalone --file C.qasm [--fuse 0|1|2] [--max-block 5] [--max-nondiag 4] [--gpu D] [--bin FILE] [--pv]\n"
+        std::cout << "usage: flatdd_gpu_standalone --file C.qasm [--fuse 0|1|2|3] [--max-block 5] [--max-nondiag 4] [--gpu D] [--bin FILE] [--pv]\n"
                      "                             [--shots N --seed S] [--time-gates] [--quiet] [--trace FILE [--trace-only]]\n";
         return args.has("file") ? 0 : 1;
     }

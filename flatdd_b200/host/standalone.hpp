@@ -21,6 +21,7 @@
 #pragma once
 
 #include "array_backend.hpp"
+#include "block_fusion.hpp"
 
 #include <algorithm>
 #include <array>
@@ -637,6 +638,61 @@ inline Block relabel(const Block& b, const std::vector<int>& map) {
 // dense block -> flat matrix DD (full depth, identity levels explicit, normalised so that equal
 // sub-blocks share nodes: a Kronecker product gets one node per level)
 // ------------------------------------------------------------------------------------------------
+// A dense block as the table the block fusion works on (block_fusion.hpp): targets = its non-diagonal qubits, context = the other
+// qubits its matrix depends on (diagonally); a qubit on which it is the identity drops out.
+inline SmallGate smallGateOf(const Block& b) {
+    const std::size_t dim = b.dim();
+    std::size_t nd = 0;
+    for (std::size_t r = 0; r < dim; ++r) {
+        for (std::size_t c = 0; c < dim; ++c) {
+            if (b.m[r * dim + c] != cplx(0, 0)) nd |= r ^ c;
+        }
+    }
+    // a diagonal qubit matters when flipping it changes some entry
+    std::size_t dep = 0;
+    for (std::size_t i = 0; i < b.qubits.size(); ++i) {
+        if ((nd >> i) & 1U) continue;
+        const std::size_t bit = std::size_t{1} << i;
+        bool differs = false;
+        for (std::size_t r = 0; r < dim && !differs; ++r) {
+            if (r & bit) continue;
+            for (std::size_t c = 0; c < dim; ++c) {
+                if (c & bit) continue;
+                if (b.m[r * dim + c] != b.m[(r | bit) * dim + (c | bit)]) {
+                    differs = true;
+                    break;
+                }
+            }
+        }
+        if (differs) dep |= bit;
+    }
+    SmallGate g;
+    std::vector<int> tPos, cPos;
+    for (std::size_t i = 0; i < b.qubits.size(); ++i) {
+        if ((nd >> i) & 1U) {
+            g.targets.push_back(b.qubits[i]);
+            tPos.push_back(static_cast<int>(i));
+        } else if ((dep >> i) & 1U) {
+            g.ctx.push_back(b.qubits[i]);
+            cPos.push_back(static_cast<int>(i));
+        }
+    }
+    const std::size_t rows = std::size_t{1} << tPos.size(), nc = std::size_t{1} << cPos.size();
+    g.table.assign(nc * rows * rows, cplx(0, 0));
+    auto spread = [](std::size_t x, const std::vector<int>& pos) {
+        std::size_t v = 0;
+        for (std::size_t i = 0; i < pos.size(); ++i) v |= ((x >> i) & 1U) << pos[i];
+        return v;
+    };
+    for (std::size_t cx = 0; cx < nc; ++cx) {
+        const std::size_t base = spread(cx, cPos); // identity qubits at 0: the entries do not depend on them
+        for (std::size_t r = 0; r < rows; ++r) {
+            for (std::size_t c = 0; c < rows; ++c) g.table[(cx * rows + r) * rows + c] = b.m[(base | spread(r, tPos)) * dim + (base | spread(c, tPos))];
+        }
+    }
+    return g;
+}
+
 class GateDDBuilder {
 public:
     explicit GateDDBuilder(int nQubits) : n_(nQubits) {}
@@ -791,6 +847,10 @@ struct FusionPolicy {
     int maxNonDiagonal = 4;  // of which non-diagonal: sizes the kernel's tile (16 segments: the tensor-core path)
     double budgetFactor = 2.2; // fuse 2: a block that touches a warp-lane qubit must stay within this many HBM passes (fdd_cost_gpu)
     double hbmGBs = 6500.0;
+    // fuse 3 (table-based dense-block fusion, the policy of GpuSwitchSimulator's --fuse 4): a block has at most blockTargets
+    // non-diagonal qubits anywhere and at most blockContext qubits it depends on diagonally
+    int blockTargets = 4;
+    int blockContext = 5;
 };
 
 class FlatStartSimulator {
@@ -798,7 +858,8 @@ public:
     FlatStartSimulator(Circuit circuit, ArrayBackend* backend) : qc_(std::move(circuit)), backend_(backend) {}
 
     // knobs with the names of the reference simulator where they still mean something
-    unsigned fuse = 0;    // 0: one launch per gate; 1: dense-block fusion with commuting open blocks; >= 2: dependency-graph dense-block fusion
+    unsigned fuse = 0;    // 0: one launch per gate; 1: dense-block fusion with commuting open blocks; 2: dependency-graph dense-block fusion
+                          // (dense matrices, GPU cost model); 3: dependency-graph fusion on block tables (block_fusion.hpp) for the tile-resident kernel
     bool verbose = true;
     bool stateLoaded = false; // the backend already holds the initial state (resume from a dumped state)
     // sharded state: the top log2(worldSize) PHYSICAL qubits are global.  Blocks are built in
@@ -836,9 +897,16 @@ public:
             timeRecord2.push_back(seconds(a0));
             ++launches;
         };
+        auto emitFlat = [&](const FlatMatDD& gate, int count) {
+            const auto a0 = std::chrono::steady_clock::now();
+            backend_->apply(gate, count);
+            kernelMsTotal += backend_->lastKernelMs();
+            timeRecord2.push_back(seconds(a0));
+            ++launches;
+        };
         if (worldSize > 1 && fuse < 2) throw std::runtime_error("a sharded state needs the dependency-graph schedule (--fuse 2)");
         if (fuse >= 2) {
-            simulateDag(emit);
+            simulateDag(emit, emitFlat);
             backend_->synchronize();
             arrayPhaseTime = seconds(t0) - gateMergingTime;
             if (verbose) {
@@ -919,7 +987,7 @@ private:
     // fuse >= 2: dependency-graph fusion.  Two operations are ordered only if they share a qubit; one block at a time is
     // grown from ALL operations whose predecessors are done (earliest first) while the policy holds — the dense-block
     // counterpart of GpuSwitchSimulator::buildScheduleDag.
-    template <class Emit> void simulateDag(Emit&& emit) {
+    template <class Emit, class EmitFlat> void simulateDag(Emit&& emit, EmitFlat&& emitFlat) {
         std::vector<const Op*> ops;
         for (const Op& op : qc_.ops) {
             if (op.kind == Op::Measure || op.kind == Op::Barrier) continue;
@@ -967,6 +1035,7 @@ private:
             }
             return false;
         };
+        std::size_t epoch = 1; // layout version: every exchange renames physical positions
         auto planExchanges = [&](std::size_t k) {
             for (int q : nonDiag[k]) {
                 const int pq = perm[static_cast<std::size_t>(q)];
@@ -994,10 +1063,16 @@ private:
                 if (victim < 0) throw std::runtime_error("no local qubit available for the exchange (gate touches too many qubits)");
                 backend_->exchange(pq, victimPos);
                 ++exchanges;
+                ++epoch;
                 std::swap(perm[static_cast<std::size_t>(q)], perm[static_cast<std::size_t>(victim)]);
             }
         };
         auto physicalBlock = [&](const Op& op) { return worldSize > 1 ? relabel(blockOf(op), perm) : blockOf(op); };
+        // fuse 3: every operation as a block table, valid while the layout (epoch) does not change
+        std::vector<SmallGate> memo(fuse >= 3 ? count : 0);
+        std::vector<std::size_t> memoEpoch(fuse >= 3 ? count : 0, 0);
+        std::size_t skipped = 0;
+        BlockDDBuilder tableBuilder(qc_.nQubits);
         std::size_t done = 0;
         while (done < count) {
             const auto m0 = std::chrono::steady_clock::now();
@@ -1006,6 +1081,97 @@ private:
                 bool any = false;
                 for (std::size_t i : ready) any = any || !needsGlobal(i);
                 if (!any) planExchanges(ready.front());
+            }
+            if (fuse >= 3) {
+                // Table-based fusion (the selection rule of GpuSwitchSimulator::buildScheduleBlocks): operations that fit the open
+                // block without a new target qubit go first, in program order; when none is left the block grows by the ready
+                // operation that adds the fewest targets; an operation that is no block of the policy's size goes through alone.
+                // Merging is BlockAcc::apply (a few thousand multiply-adds), a DD is built once per emitted block.
+                BlockAcc block;
+                int blockOps = 0;
+                long wide = -1; // ready-list slot of an operation that has to go through on its own
+                bool progress = true;
+                while (progress) {
+                    progress = false;
+                    long pick = -1;
+                    std::size_t pickGrowth = 99;
+                    for (std::size_t r = 0; r < ready.size(); ++r) {
+                        const std::size_t i = ready[r];
+                        if (needsGlobal(i)) continue;
+                        if (memoEpoch[i] != epoch) {
+                            memo[i] = smallGateOf(physicalBlock(*ops[i]));
+                            memoEpoch[i] = epoch;
+                        }
+                        const SmallGate& g = memo[i];
+                        if (g.isIdentity()) {
+                            pick = static_cast<long>(r);
+                            pickGrowth = 0;
+                            break;
+                        }
+                        if (static_cast<int>(g.targets.size()) > policy.blockTargets || static_cast<int>(g.ctx.size()) > policy.blockContext) {
+                            if (blockOps == 0 && pick < 0) {
+                                pick = static_cast<long>(r);
+                                pickGrowth = 98;
+                            }
+                            continue;
+                        }
+                        std::vector<int> t2, c2;
+                        block.merged(g, t2, c2);
+                        if (static_cast<int>(t2.size()) > policy.blockTargets || static_cast<int>(c2.size()) > policy.blockContext) continue;
+                        const std::size_t growth = t2.size() - block.targets.size();
+                        if (growth < pickGrowth) {
+                            pick = static_cast<long>(r);
+                            pickGrowth = growth;
+                            if (growth == 0) break;
+                        }
+                    }
+                    if (pick < 0) break;
+                    const std::size_t i = ready[static_cast<std::size_t>(pick)];
+                    if (pickGrowth == 98) {
+                        wide = pick;
+                        break;
+                    }
+                    if (!memo[i].isIdentity()) {
+                        block.apply(memo[i]);
+                        ++blockOps;
+                    } else {
+                        ++skipped;
+                    }
+                    ready.erase(ready.begin() + pick);
+                    for (std::size_t nxt : succ[i]) {
+                        if (--indeg[nxt] == 0) ready.insert(std::lower_bound(ready.begin(), ready.end(), nxt), nxt);
+                    }
+                    ++done;
+                    progress = true;
+                }
+                if (wide >= 0) {
+                    const std::size_t i = ready[static_cast<std::size_t>(wide)];
+                    Open alone{physicalBlock(*ops[i]), 1};
+                    ready.erase(ready.begin() + wide);
+                    for (std::size_t nxt : succ[i]) {
+                        if (--indeg[nxt] == 0) ready.insert(std::lower_bound(ready.begin(), ready.end(), nxt), nxt);
+                    }
+                    ++done;
+                    gateMergingTime += seconds(m0);
+                    emit(alone);
+                    continue;
+                }
+                if (blockOps == 0) {
+                    gateMergingTime += seconds(m0);
+                    if (done >= count) break; // only identities were left
+                    if (skipped > 0) {
+                        skipped = 0;
+                        continue;
+                    }
+                    throw std::runtime_error("dense-block fusion made no progress");
+                }
+                skipped = 0;
+                const bool identity = block.targets.empty() && block.ctx.empty() && block.table[0] == cplx(1.0, 0.0);
+                FlatMatDD gate;
+                if (!identity) gate = tableBuilder.build(block.targets, block.ctx, block.table);
+                gateMergingTime += seconds(m0);
+                if (!identity) emitFlat(gate, blockOps);
+                continue;
             }
             Open current;
             bool progress = true;

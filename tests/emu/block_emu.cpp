@@ -55,16 +55,28 @@ template <int K> void applyBlockEmu(const BlockDesc& b, const double* table, std
                 for (int e = 0; e < 2; ++e) {
                     const int row = 8 * mt + (lane >> 2); // sigma index
                     const int n = 2 * (lane & 3) + e;     // fragment column
-                    cplx acc = 0;
+                    // the kernel's three real products (BlockRunner::issue): K1 = Mr (Yr + Yi) first, then the Re chain
+                    // K1 + (-(Mr + Mi)) Yi and the Im chain K1 + (Mi - Mr) Yr continue from it, K slabs in order
+                    double k1 = 0.0;
                     for (int kt = 0; kt < KTL; ++kt) {
                         for (int kk = 0; kk < 4; ++kk) {
                             const int col = 4 * kt + kk; // sigma index
                             const size_t at = 2 * (static_cast<size_t>(b.canon[row]) * ROWS + b.canon[col]);
-                            const cplx a(m[at], m[at + 1]);
-                            acc += a * y[kt][4 * n + kk]; // the lane that holds B[kk][n] is 4 n + kk
+                            const cplx yv = y[kt][4 * n + kk]; // the lane that holds B[kk][n] is 4 n + kk
+                            k1 += m[at] * (yv.real() + yv.imag());
                         }
                     }
-                    d[lane][e] = acc;
+                    double zr = k1, zi = k1;
+                    for (int kt = 0; kt < KTL; ++kt) {
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const int col = 4 * kt + kk;
+                            const size_t at = 2 * (static_cast<size_t>(b.canon[row]) * ROWS + b.canon[col]);
+                            const cplx yv = y[kt][4 * n + kk];
+                            zr += (-m[at] - m[at + 1]) * yv.imag();
+                            zi += (m[at + 1] - m[at]) * yv.real();
+                        }
+                    }
+                    d[lane][e] = cplx(zr, zi);
                 }
             }
             int hits[2][4][8] = {};

@@ -34,7 +34,7 @@ def run(circuit: Path, fuse: int, extra=()):
 
 
 @pytest.mark.skipif(not CLI.exists(), reason="build/flatdd_gpu_standalone not built")
-@pytest.mark.parametrize("fuse", [0, 1, 2])
+@pytest.mark.parametrize("fuse", [0, 1, 2, 3])
 @pytest.mark.parametrize("name,golden", SMALL)
 def test_standalone_final_state(name, golden, fuse):
     full, re, im = run(ROOT / "tests" / "circuits" / f"{name}.qasm", fuse)

@@ -40,7 +40,7 @@ def run_trace_only(circuit: Path, fuse: int, extra=()):
     return n, records, stats
 
 
-@pytest.mark.parametrize("fuse", [0, 1, 2])
+@pytest.mark.parametrize("fuse", [0, 1, 2, 3])
 @pytest.mark.parametrize("name,golden", CASES)
 def test_standalone_trace_reproduces_the_reference_state(name, golden, fuse):
     n, records, stats = run_trace_only(ROOT / "tests" / "circuits" / f"{name}.qasm", fuse)
@@ -125,7 +125,7 @@ def test_reader_registers_broadcast_and_expressions():
                        ([1], u3(math.sin(0.3), math.cos(0.2), math.sqrt(2))), ([0, 4], cx), ([1, 4], cx)]:
         ref = B.apply_dense(5, targets, m, ref)
     assert np.max(np.abs(psi - ref)) < 1e-14
-    for fuse in (1, 2):
+    for fuse in (1, 2, 3):
         _, fused, _ = _final_state(text, fuse)
         assert np.max(np.abs(fused - ref)) < 1e-14
 
@@ -167,7 +167,7 @@ def test_controlled_and_two_target_gates_match_dense_algebra():
     for targets, m in steps:
         ref = B.apply_dense(6, targets, m, ref)
     assert np.max(np.abs(psi - ref)) < 1e-14
-    for fuse in (1, 2):
+    for fuse in (1, 2, 3):
         _, fused, _ = _final_state(text, fuse)
         assert np.max(np.abs(fused - ref)) < 1e-13
 
@@ -260,7 +260,7 @@ def test_fusion_is_state_preserving_on_random_circuits(seed):
         q = Path(tmp) / "c.qasm"
         q.write_text(text)
         for fuse, extra in [(1, ()), (2, ()), (1, ("--max-block", "3", "--max-nondiag", "2")), (2, ("--max-block", "6", "--max-nondiag", "3")),
-                            (2, ("--budget", "1.3"))]:
+                            (2, ("--budget", "1.3")), (3, ())]:
             _, records, stats = run_trace_only(q, fuse, extra)
             re, im = pyoracle.replay_trace(records)
             assert np.max(np.abs((re + 1j * im) - ref)) < 1e-12, (fuse, extra)
@@ -268,7 +268,8 @@ def test_fusion_is_state_preserving_on_random_circuits(seed):
         if n - 1 >= 5:  # two shards need five local qubits
             from flatdd_b200.sharded import replay, to_logical_order
             from tests.test_sharded_cpu import GlobalModel
-            _, records, _ = run_trace_only(q, 2, ("--world", "2"))
-            model = GlobalModel(n, n - 1)
-            l2p = replay(records, model, n)
-            assert np.max(np.abs(to_logical_order(model.re + 1j * model.im, l2p) - ref)) < 1e-12
+            for fuse in (2, 3):
+                _, records, _ = run_trace_only(q, fuse, ("--world", "2"))
+                model = GlobalModel(n, n - 1)
+                l2p = replay(records, model, n)
+                assert np.max(np.abs(to_logical_order(model.re + 1j * model.im, l2p) - ref)) < 1e-12, fuse
