@@ -308,7 +308,8 @@ def measure(workload: str, args, steps: int, warmup: int, with_e2e: bool) -> dic
         ev[3 * s + 2].record(stream)
     barrier()
     launches = ctx.launch_count() - launches0
-    tensor_launches = ctx.get_option("tensor_core_launches") - tensor0
+    # launches that ran FP64 tensor-core code: the older tile kernel's DMMA instantiation and every pass of the dense-block kernel
+    tensor_launches = (ctx.get_option("tensor_core_launches") - tensor0) + (ctx.get_option("block_launches") - passes0)
     block_passes = (ctx.get_option("block_launches") - passes0) // steps   # passes of the tile-resident dense-block kernel per step
     blocks_applied = (ctx.get_option("blocks_applied") - blocks0) // steps  # fused gates those passes applied
     # FP64 tensor-core work of a step: a 2^k x 2^k complex block is three real products of 2^k x 2^k x 2^n_local each

@@ -1324,9 +1324,9 @@ int fdd_apply_many(fdd_ctx* ctx, const fdd_matdd* gates, int count) {
                 if (gates[i].n_qubits != ctx->n) throw std::invalid_argument("gate has " + std::to_string(gates[i].n_qubits) + " qubits, context has " + std::to_string(ctx->n));
             }
             // the DD -> block expansion of every gate is host work (a quarter of a millisecond per fused gate of supremacy_n26):
-            // on a few threads, so that the device does not wait for it
+            // on up to sixteen threads, so that the device does not wait for it
             std::vector<std::unique_ptr<DenseBlock>> blocks(static_cast<size_t>(count));
-            const int nThreads = std::max(1, std::min({count / 4, 8, static_cast<int>(std::thread::hardware_concurrency())}));
+            const int nThreads = std::max(1, std::min({count / 3, 16, static_cast<int>(std::thread::hardware_concurrency())}));
             if (nThreads > 1) {
                 std::vector<std::thread> pool;
                 std::vector<std::exception_ptr> errors(static_cast<size_t>(nThreads));

@@ -64,6 +64,22 @@ bool denseBlockFromDD(const fdd_matdd& g, DenseBlock& out, int maxCtx) {
     const std::size_t rows = out.rows();
     out.table.assign((std::size_t{2} * rows * rows) << out.ctx.size(), 0.0);
     if (isZero(g.root_weight)) return true;
+    // Below its lowest target / context level a path is a chain of identity-like nodes.  Where every weight on that chain is
+    // exactly 1 the walk can stop at the top of the chain: multiplying by 1 changes nothing, whatever the order (normalised
+    // gate DDs are of this kind; the chain is 20 of the 26 levels of a supremacy_n26 block and was most of the frames).
+    std::vector<uint8_t> tailOne(nNodes, 0);
+    {
+        std::vector<int32_t> order; // reachable nodes by ascending level: successors first
+        for (std::size_t u = 0; u < nNodes; ++u) {
+            if (reach[u]) order.push_back(static_cast<int32_t>(u));
+        }
+        std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return g.level[a] < g.level[b]; });
+        for (int32_t u : order) {
+            const int v = g.level[u];
+            if (levelClass[static_cast<std::size_t>(v)] != 0 || W(u, 0)[0] != 1.0 || W(u, 0)[1] != 0.0) continue;
+            tailOne[static_cast<std::size_t>(u)] = (v == 0 || (C(u, 0) >= 0 && tailOne[static_cast<std::size_t>(C(u, 0))])) ? 1 : 0;
+        }
+    }
     // depth-first over the non-zero paths; every (context, row, column) is one path
     struct Frame {
         int32_t node;
@@ -75,7 +91,7 @@ bool denseBlockFromDD(const fdd_matdd& g, DenseBlock& out, int maxCtx) {
     while (!work.empty()) {
         const Frame f = work.back();
         work.pop_back();
-        if (f.node == FDD_TERMINAL) {
+        if (f.node == FDD_TERMINAL || tailOne[static_cast<std::size_t>(f.node)]) {
             const std::size_t at = 2 * ((static_cast<std::size_t>(f.ctx) * rows + f.row) * rows + f.col);
             out.table[at] = f.w.re;
             out.table[at + 1] = f.w.im;
