@@ -270,10 +270,20 @@ def measure(workload: str, args, steps: int, warmup: int, with_e2e: bool) -> dic
             dist.barrier(device_ids=[local_rank])
             torch.cuda.synchronize()
 
+    fuse_exchange = method == 0 and args.fuse_exchange != 0
+
     def step_resident(exchange_events=None):
-        for s in sched:
+        skip = False
+        for at, s in enumerate(sched):
+            if skip:  # this exchange went along with the stretch before it (fdd_gate_apply_many_exchange)
+                skip = False
+                continue
             if s[0] == "g":
-                ctx.apply_compiled_many(s[1])
+                if fuse_exchange and at + 1 < len(sched) and sched[at + 1][0] == "x":
+                    ctx.apply_compiled_many_exchange(s[1], sched[at + 1][1], sched[at + 1][2])
+                    skip = True
+                else:
+                    ctx.apply_compiled_many(s[1])
             elif s[0] == "x":
                 if exchange_events is not None:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -299,6 +309,7 @@ def measure(workload: str, args, steps: int, warmup: int, with_e2e: bool) -> dic
     launches0 = ctx.launch_count()
     tensor0 = ctx.get_option("tensor_core_launches")
     passes0, blocks0 = ctx.get_option("block_launches"), ctx.get_option("blocks_applied")
+    fused0 = ctx.get_option("fused_exchanges")
     barrier()
     for s in range(steps):
         ev[3 * s].record(stream)
@@ -308,6 +319,7 @@ def measure(workload: str, args, steps: int, warmup: int, with_e2e: bool) -> dic
         ev[3 * s + 2].record(stream)
     barrier()
     launches = ctx.launch_count() - launches0
+    n_fused = (ctx.get_option("fused_exchanges") - fused0) // steps  # exchanges that rode on the pass before them (no kernel of their own)
     # launches that ran FP64 tensor-core code: the older tile kernel's DMMA instantiation and every pass of the dense-block kernel
     tensor_launches = (ctx.get_option("tensor_core_launches") - tensor0) + (ctx.get_option("block_launches") - passes0)
     block_passes = (ctx.get_option("block_launches") - passes0) // steps   # passes of the tile-resident dense-block kernel per step
@@ -344,6 +356,10 @@ def measure(workload: str, args, steps: int, warmup: int, with_e2e: bool) -> dic
             for r in records[1:]:
                 if r.kind == 2:
                     stretch.append(r.dd)
+                    continue
+                if stretch and r.kind == 3 and fuse_exchange:
+                    ctx.apply_many_exchange(stretch, r.exchange[0], r.exchange[1])
+                    stretch = []
                     continue
                 if stretch:
                     ctx.apply_many(stretch)
@@ -413,7 +429,7 @@ def measure(workload: str, args, steps: int, warmup: int, with_e2e: bool) -> dic
     # DMAVM time: the step body minus the exchanges.  One LAUNCH of the dense-block kernel is one pass over the state that
     # applies one or more fused gates to a tile held in shared memory; the algorithmic bytes of a launch are SURVEY.md 8(d)'s
     # per-unit figure (32 * 2^n per applied fused gate) times the fused gates the launch applies.
-    dmavm_ms = body_mean - exch_mean_ms * n_exch
+    dmavm_ms = body_mean - exch_mean_ms * (n_exch - n_fused)  # (a fused exchange is part of its pass: the pass's time includes the transfer)
     launch_ms = dmavm_ms / max(1, n_gates)  # per fused gate
     other_launches = n_gates - blocks_applied  # fused gates that took one of the older kernels: one launch each
     passes = block_passes + other_launches
@@ -454,10 +470,13 @@ def measure(workload: str, args, steps: int, warmup: int, with_e2e: bool) -> dic
                       "seconds_per_circuit": e2e_s, "steps": e2e_steps}
     if world > 1 and n_exch:
         half_bytes = 8.0 * local_dim
-        gbs = half_bytes / (exch_mean_ms * 1e-3) / 1e9
-        res["exchange"] = {"per_step": n_exch, "bytes_each_way_per_gpu": half_bytes, "ms_mean": exch_mean_ms, "gbs_per_direction": gbs,
-                           "frac_of_nvlink_nominal_900": gbs / 900.0, "frac_of_nvlink_measured_770": gbs / 770.0,
-                           "method": "peer-memory kernel (flags in peer memory, no NCCL call)" if method == 0 else "NCCL send/recv + D2D copy"}
+        gbs = half_bytes / (exch_mean_ms * 1e-3) / 1e9 if exch_mean_ms > 0 else None
+        res["exchange"] = {"per_step": n_exch, "fused_into_the_preceding_pass": int(n_fused), "own_kernel": int(n_exch - n_fused),
+                           "bytes_each_way_per_gpu": half_bytes, "ms_mean": exch_mean_ms if gbs else None, "gbs_per_direction": gbs,
+                           "frac_of_nvlink_nominal_900": gbs / 900.0 if gbs else None, "frac_of_nvlink_measured_770": gbs / 770.0 if gbs else None,
+                           "note": "ms / GB/s are those of the exchanges that ran as a kernel of their own; a fused exchange is stored by the pass before it "
+                                   "straight into the partner's buffer (peer memory) and has no time of its own",
+                           "method": "peer-memory kernels (flags in peer memory, no NCCL call)" if method == 0 else "NCCL send/recv + D2D copy"}
     return res
 
 
@@ -581,6 +600,7 @@ def main() -> int:
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default=WORKLOAD, help="supremacy_n26 (default), supremacy_n20, knn_n31_f0, ... (needs its boundary trace)")
     ap.add_argument("--exchange-method", type=int, default=0, help="0 = peer-memory kernel, 1 = NCCL send/recv")
+    ap.add_argument("--fuse-exchange", type=int, default=1, help="1: a schedule stretch and the exchange after it cross the boundary in one call (fdd_*_apply_many_exchange)")
     ap.add_argument("--extra", default="auto", help="extra workloads timed in the same run: auto (knn_n31_f0 at 2/4/8 GPUs, synth_n34 at 8), none, or a comma list")
     ap.add_argument("--option", action="append", default=[], help="experiments: library tunable key=value (fdd_set_option), repeatable")
     args = ap.parse_args()

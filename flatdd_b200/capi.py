@@ -27,7 +27,7 @@ class FlatDDError(RuntimeError):
 EXPORTS = [
     "fdd_version", "fdd_last_error", "fdd_device_count", "fdd_create", "fdd_create_sharded", "fdd_destroy",
     "fdd_n_qubits", "fdd_n_local_qubits", "fdd_synchronize", "fdd_set_option", "fdd_get_option", "fdd_comm_unique_id", "fdd_comm_init",
-    "fdd_exchange_qubits", "fdd_relabel_qubits", "fdd_barrier",
+    "fdd_exchange_qubits", "fdd_apply_many_exchange", "fdd_gate_apply_many_exchange", "fdd_relabel_qubits", "fdd_barrier",
     "fdd_convert", "fdd_apply", "fdd_apply_many", "fdd_block_from_matdd", "fdd_gate_compile", "fdd_gate_apply", "fdd_gate_apply_many", "fdd_gate_free", "fdd_gate_info",
     "fdd_ddarr_multiply", "fdd_mac_count", "fdd_cost_ip", "fdd_cost_op1", "fdd_cost_gpu", "fdd_matdd_info", "fdd_get_state",
     "fdd_set_state", "fdd_set_zero_state", "fdd_get_amplitudes", "fdd_get_amplitudes_at", "fdd_norm2", "fdd_sample", "fdd_state_device_ptr",
@@ -262,6 +262,16 @@ class Context:
             return
         arr = (type(gates[0].as_c()) * len(gates))(*[g.as_c() for g in gates])
         self.L.check(self.L.lib.fdd_apply_many(self._h, arr, len(gates)))
+
+    def apply_many_exchange(self, gates, global_physical_bit: int, local_physical_bit: int):
+        """A stretch of host tables and the exchange that follows it in one boundary call (the library fuses them when it can)."""
+        gates = list(gates)
+        arr = (type(gates[0].as_c()) * len(gates))(*[g.as_c() for g in gates]) if gates else None
+        self.L.check(self.L.lib.fdd_apply_many_exchange(self._h, arr, len(gates), int(global_physical_bit), int(local_physical_bit)))
+
+    def apply_compiled_many_exchange(self, gates, global_physical_bit: int, local_physical_bit: int):
+        arr = (ctypes.c_void_p * len(gates))(*[g._h for g in gates]) if gates else None
+        self.L.check(self.L.lib.fdd_gate_apply_many_exchange(self._h, arr, len(gates), int(global_physical_bit), int(local_physical_bit)))
 
     def compile(self, gate: FlatDD) -> CompiledGate:
         c = gate.as_c()

@@ -133,6 +133,8 @@ struct fdd_ctx {
                                // 2^13 fills the shared memory with one buffer: measured slower than separate passes)
     int blockWarps = 0;       // experiments: 16 = sixteen warps per CTA with one unit per iteration
     int blockUnits = 2;       // units per iteration and warp (2: twelve independent tensor-core chains, one CTA per SM; 1: two CTAs per SM)
+    int blockFuseExchange = 1; // fdd_*_apply_many_exchange: the last pass of the stretch writes the traded half into the partner's buffer
+    uint64_t fusedExchanges = 0;
     int blockReorder = 1;      // blocks move up over gates they commute with to share a pass (orderForPasses)
     int blockTablesShared = 1; // multi-block passes keep the blocks' matrix tables in shared memory when they fit
     int blockBuffers = 3;     // tile buffers per CTA when they fit (copy-in, tensor-core work and copy-out of consecutive tiles overlap)
@@ -564,7 +566,17 @@ bool usesBlockPath(const fdd_ctx* c, const fdd_gate* g) { return c->blockKernel 
 
 // One pass of the tile-resident kernel over gates[0..count) (all of them blocks).  Returns false when they do not fit one
 // tile or the fragment shape cannot be planned; nothing has been launched then.
-bool launchPass(fdd_ctx* c, const fdd_gate* const* gates, int count, bool cachePlan) {
+// SWAP(global physical bit pg, local physical bit pl) that follows a stretch of gates: fused into the stretch's last pass when
+// that pass runs on the warp-specialised block kernel and pl is above the lane bits (PassParams::zPeer)
+struct ExchangeSpec {
+    int pg = 0, pl = 0;
+    bool done = false;
+};
+bool canFuseExchange(const fdd_ctx* c, const ExchangeSpec& ex) {
+    return c->blockFuseExchange != 0 && c->exchangeFlags != 0 && c->comm != nullptr && c->blockWs != 0 && ex.pl >= kLaneBits && ex.pl < c->nLocal;
+}
+
+bool launchPass(fdd_ctx* c, const fdd_gate* const* gates, int count, bool cachePlan, ExchangeSpec* ex = nullptr) {
     if (!c->hasState) throw std::logic_error("no state: call fdd_convert / fdd_set_state / fdd_set_zero_state first");
     std::vector<uint64_t> key;
     if (cachePlan) {
@@ -662,6 +674,21 @@ bool launchPass(fdd_ctx* c, const fdd_gate* const* gates, int count, bool cacheP
     }
     planned.params.y = c->buf[c->cur];
     planned.params.z = c->buf[c->cur ^ 1];
+    planned.params.zPeer = nullptr;
+    if (ex != nullptr && planned.ws && canFuseExchange(c, *ex)) {
+        const int gbit = ex->pg - c->nLocal;
+        const int partner = c->rank ^ (1 << gbit);
+        planned.params.zPeer = const_cast<double2*>(c->peerBuf[c->cur ^ 1][partner]);
+        planned.params.exchSegBit = ex->pl - kLaneBits;
+        planned.params.exchMyBit = static_cast<uint32_t>((c->rank >> gbit) & 1);
+        planned.params.exchEpoch = ++c->exchangeEpoch;
+        planned.params.exchMyFlags = c->dFlags;
+        planned.params.exchPartnerFlags = c->peerFlags[partner];
+        planned.params.exchCounter = reinterpret_cast<unsigned int*>(c->dFlags + 2);
+        ex->done = true;
+        c->exchanges++;
+        c->fusedExchanges++;
+    }
     static const char* skipEnv = std::getenv("FLATDD_B200_BLOCK_SKIP");
     planned.params.debugSkip = skipEnv != nullptr ? static_cast<uint32_t>(std::atoi(skipEnv)) : 0u;
     static const bool clocksEnv = std::getenv("FLATDD_B200_BLOCK_CLOCKS") != nullptr;
@@ -777,7 +804,9 @@ std::vector<const fdd_gate*> orderForPasses(const fdd_ctx* c, const fdd_gate* co
 }
 
 // gates[0..count) in order: consecutive blocks share a pass while they fit one tile, everything else takes the older kernels
-void applyGates(fdd_ctx* c, const fdd_gate* const* gatesIn, int count, bool cachePlan) {
+extern "C" void exchangeBits(fdd_ctx* c, int pg, int pl, int method); // (defined among the extern "C" entry points below)
+
+void applyGates(fdd_ctx* c, const fdd_gate* const* gatesIn, int count, bool cachePlan, ExchangeSpec* ex = nullptr) {
     std::vector<const fdd_gate*> ordered;
     const fdd_gate* const* gates = gatesIn;
     if (c->blockReorder != 0 && count > 2) {
@@ -805,12 +834,17 @@ void applyGates(fdd_ctx* c, const fdd_gate* const* gatesIn, int count, bool cach
         }
         // a group whose fragment shapes cannot be planned shrinks from the back; a single block that cannot falls back
         int n = j - i;
-        while (n >= 1 && !launchPass(c, gates + i, n, cachePlan)) --n;
+        // (the pass that ends the stretch takes the exchange that follows it along)
+        while (n >= 1 && !launchPass(c, gates + i, n, cachePlan, i + n == count ? ex : nullptr)) --n;
         if (n == 0) {
             walkWithTables(c, gates[i]);
             n = 1;
         }
         i += n;
+    }
+    if (ex != nullptr && !ex->done) { // the stretch did not end in a pass that could take it: the exchange kernel
+        exchangeBits(c, ex->pg, ex->pl, 0);
+        ex->done = true;
     }
 }
 
@@ -954,6 +988,7 @@ int fdd_set_option(fdd_ctx* ctx, const char* key, long value) {
         else if (k == "block_buffers") ctx->blockBuffers = static_cast<int>(value);
         else if (k == "block_tables_shared") ctx->blockTablesShared = static_cast<int>(value);
         else if (k == "block_reorder") ctx->blockReorder = static_cast<int>(value);
+        else if (k == "block_fuse_exchange") ctx->blockFuseExchange = static_cast<int>(value);
         else if (k == "block_warps") ctx->blockWarps = static_cast<int>(value);
         else if (k == "block_units") ctx->blockUnits = static_cast<int>(value);
         else if (k == "block_ws") ctx->blockWs = static_cast<int>(value);
@@ -990,6 +1025,8 @@ int fdd_get_option(const fdd_ctx* ctx, const char* key, long* value) {
         else if (k == "block_buffers") *value = ctx->blockBuffers;
         else if (k == "block_tables_shared") *value = ctx->blockTablesShared;
         else if (k == "block_reorder") *value = ctx->blockReorder;
+        else if (k == "block_fuse_exchange") *value = ctx->blockFuseExchange;
+        else if (k == "fused_exchanges") *value = static_cast<long>(ctx->fusedExchanges);
         else if (k == "block_warps") *value = ctx->blockWarps;
         else if (k == "block_units") *value = ctx->blockUnits;
         else if (k == "block_ws") *value = ctx->blockWs;
@@ -1270,6 +1307,27 @@ int fdd_gate_apply_many(fdd_ctx* ctx, const fdd_gate* const* gates, int count) {
     });
 }
 
+static void checkExchangeArgs(const fdd_ctx* ctx, int global_physical_bit, int local_physical_bit) {
+    if (ctx->world == 1) throw std::logic_error("context is not sharded");
+    if (global_physical_bit < ctx->nLocal || global_physical_bit >= ctx->n) throw std::invalid_argument("not a global physical bit");
+    if (local_physical_bit < 0 || local_physical_bit >= ctx->nLocal) throw std::invalid_argument("not a local physical bit");
+    if (ctx->comm == nullptr) throw std::logic_error("shards are not connected: call fdd_comm_init first");
+}
+
+int fdd_gate_apply_many_exchange(fdd_ctx* ctx, const fdd_gate* const* gates, int count, int global_physical_bit, int local_physical_bit) {
+    return guarded([&] {
+        if (ctx == nullptr || (gates == nullptr && count > 0)) throw std::invalid_argument("null argument");
+        checkExchangeArgs(ctx, global_physical_bit, local_physical_bit);
+        useDevice(ctx);
+        for (int i = 0; i < count; ++i) {
+            if (gates[i] == nullptr) throw std::invalid_argument("null gate in the list");
+        }
+        ExchangeSpec ex{global_physical_bit, local_physical_bit, false};
+        applyGates(ctx, gates, count, true, &ex);
+        swapPermutationEntries(ctx, global_physical_bit, local_physical_bit);
+    });
+}
+
 int fdd_gate_free(fdd_gate* gate) {
     freeGate(gate, nullptr);
     return FDD_OK;
@@ -1311,8 +1369,8 @@ int fdd_matdd_info(const fdd_matdd* gate, const char* key, long* value) {
     });
 }
 
-int fdd_apply_many(fdd_ctx* ctx, const fdd_matdd* gates, int count) {
-    return guarded([&] {
+static void applyManyHost(fdd_ctx* ctx, const fdd_matdd* gates, int count, ExchangeSpec* ex) {
+    {
         if (ctx == nullptr || (gates == nullptr && count > 0)) throw std::invalid_argument("null argument");
         useDevice(ctx);
         std::vector<fdd_gate*> owned;
@@ -1354,12 +1412,26 @@ int fdd_apply_many(fdd_ctx* ctx, const fdd_matdd* gates, int count) {
                 g->source = &gates[i]; // the older kernels' tables are only made if a launch needs them
                 uploadBlock(ctx, g, std::move(blocks[static_cast<size_t>(i)]));
             }
-            applyGates(ctx, owned.data(), count, false);
+            applyGates(ctx, owned.data(), count, false, ex);
         } catch (...) {
             release();
             throw;
         }
         release();
+    }
+}
+
+int fdd_apply_many(fdd_ctx* ctx, const fdd_matdd* gates, int count) {
+    return guarded([&] { applyManyHost(ctx, gates, count, nullptr); });
+}
+
+int fdd_apply_many_exchange(fdd_ctx* ctx, const fdd_matdd* gates, int count, int global_physical_bit, int local_physical_bit) {
+    return guarded([&] {
+        if (ctx == nullptr) throw std::invalid_argument("null argument");
+        checkExchangeArgs(ctx, global_physical_bit, local_physical_bit);
+        ExchangeSpec ex{global_physical_bit, local_physical_bit, false};
+        applyManyHost(ctx, gates, count, &ex);
+        swapPermutationEntries(ctx, global_physical_bit, local_physical_bit);
     });
 }
 

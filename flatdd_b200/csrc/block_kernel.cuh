@@ -422,6 +422,12 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
         for (uint32_t t = blockIdx.x + i * gridDim.x; t < p.nTiles; t += blockDim.x * gridDim.x, i += blockDim.x) tileSeg[i] = spreadAround(t, p.tileMask);
     }
     unsigned char* tableArea = smemRaw + blockPassTableArea(p.tileBits, nBuffers, p.nBlocks, maxUnits, (p.nTiles + gridDim.x - 1) / gridDim.x);
+    if (p.zPeer != nullptr && threadIdx.x == 0) {
+        // fused exchange: this kernel runs after the shard's earlier launches, so the buffer the partner is about to write into has
+        // been read to the end; nothing may be stored into the partner's buffer before the partner says the same
+        if (blockIdx.x == 0) st_release_sys(p.exchMyFlags, p.exchEpoch);
+        while (ld_acquire_sys(p.exchPartnerFlags) < p.exchEpoch) __nanosleep(64);
+    }
     if (threadIdx.x == 0) {
         for (int b = 0; b < nBuffers; ++b) {
             mbarInit(full + b, 32 * kMemoryWarps);
@@ -476,6 +482,22 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
             mbarWait(done + buf, phase);
             if (p.debugSkip & 2u) return;
             const double2* src = tiles + static_cast<size_t>(buf) * tileElems;
+            if (p.zPeer != nullptr) {
+                // fused exchange: a segment whose traded bit differs from this shard's global bit now belongs to the partner, at the
+                // index with that bit flipped
+                double2* zFar = static_cast<double2*>(p.zPeer);
+                const uint32_t base = tileSeg[it];
+                const uint32_t bit = 1u << p.exchSegBit;
+#pragma unroll 4
+                for (uint32_t j = mw; j < nSegTile; j += kMemoryWarps) {
+                    const uint2 e = segTab[j];
+                    const uint32_t seg = base | e.x;
+                    const bool stays = ((seg >> p.exchSegBit) & 1u) == p.exchMyBit;
+                    double2* to = stays ? z + (static_cast<uint64_t>(seg) << kLaneBits) : zFar + (static_cast<uint64_t>(seg ^ bit) << kLaneBits);
+                    st_stream(to + lane, src[e.y ^ laneSwz]);
+                }
+                return;
+            }
             double2* dst = z + (static_cast<uint64_t>(tileSeg[it]) << kLaneBits) + lane;
 #pragma unroll 4
             for (uint32_t j = mw; j < nSegTile; j += kMemoryWarps) {
@@ -507,6 +529,23 @@ __global__ void __launch_bounds__(kBlockThreads, 1) dmavm_block_ws_kernel(const 
             }
         }
         cp_async_wait<0>();
+        if (p.zPeer != nullptr) {
+            // this thread's stores into the partner's buffer are performed before the CTA counts itself as finished; the last CTA
+            // tells the partner and keeps the kernel alive until the partner's stores into THIS shard's buffer are complete too
+            // (the next launch reads them)
+            __threadfence_system();
+            asm volatile("bar.sync 2, %0;\n" ::"n"(32 * kMemoryWarps) : "memory");
+            if (threadIdx.x == 32 * kComputeWarps) {
+                __threadfence();
+                const unsigned int arrived = atomicAdd(p.exchCounter, 1u);
+                if (arrived == gridDim.x - 1) {
+                    *p.exchCounter = 0; // for the next exchange (every CTA has arrived)
+                    __threadfence_system();
+                    st_release_sys(p.exchMyFlags + 1, p.exchEpoch);
+                    while (ld_acquire_sys(p.exchPartnerFlags + 1) < p.exchEpoch) __nanosleep(64);
+                }
+            }
+        }
     } else {
         // =================== compute warps ==================================================================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");

@@ -99,6 +99,16 @@ struct PassParams {
     uint32_t tableSmem[kPassMaxBlocks]; // byte offset of the block's matrix table in the CTA's shared-memory table area when the pass
                             // stages it there (multi-block passes: every (tile, block) visit reloads the warp's A fragments, and from
                             // global memory that is an L2 round trip under full HBM load), else kTableInGlobal
+    // Fused exchange (multi-GPU): the pass that precedes SWAP(global bit, local bit pl >= 5) writes the half of its result that
+    // changes owner straight into the partner shard's buffer (peer stores over NVLink, per 512-byte segment) and keeps the other
+    // half, so the transfer runs under the pass instead of after it.  Ordering: the flag words of comm.cuh.
+    void* zPeer;                     // the partner's destination buffer (peer mapped), null: no exchange
+    int32_t exchSegBit;              // pl - 5: the segment-index bit that is traded
+    uint32_t exchMyBit;              // this shard's value of the global bit: segments with that value of the traded bit stay
+    uint32_t exchEpoch;
+    uint32_t* exchMyFlags;           // [0] my earlier launches are complete, [1] my stores into the partner's buffer are complete
+    const uint32_t* exchPartnerFlags;
+    unsigned int* exchCounter;       // CTAs that have finished their stores
     uint32_t debugSkip;     // experiments (FLATDD_B200_BLOCK_SKIP): bit 0 = no tensor-core work, bit 1 = no global loads/stores
     long long* debugClocks; // experiments (FLATDD_B200_BLOCK_CLOCKS): per compute warp {cycles waiting for tiles, cycles in the blocks, total}
     BlockDesc blocks[kPassMaxBlocks];

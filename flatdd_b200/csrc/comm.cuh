@@ -112,12 +112,7 @@ __global__ void __launch_bounds__(256) exchange_p2p_kernel(const double2* __rest
 //      rank's stream overwrites the buffer the partner has been reading.
 // Replaces two stream-ordered one-element ncclAllReduce "barriers" (about 55 us of the 164 us per exchange at 8 GPUs and
 // 64 MiB messages).  Epochs only grow; every rank takes part in every exchange, so they agree on e.
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
+// (st_release_sys / ld_acquire_sys: kernels.cuh)
 template <int U>
 __global__ void __launch_bounds__(256) exchange_p2p_flag_kernel(const double2* __restrict__ mine, const double2* __restrict__ partner,
                                                                 double2* __restrict__ out, uint64_t n, int pl, int myBit, uint32_t* myFlags,

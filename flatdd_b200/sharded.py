@@ -21,12 +21,24 @@ class ShardBackend(Protocol):
 def replay(records: Iterable[TraceRecord], backend: ShardBackend, n_qubits: int) -> List[int]:
     """Runs every record on the backend; returns the final logical->physical qubit map."""
     phys_to_logical = list(range(n_qubits))
-    for rec in records:
+    records = list(records)
+    fuse = getattr(backend, "apply_then_exchange", None)  # a gate and the exchange that follows it in one boundary call
+    skip = False
+    for at, rec in enumerate(records):
+        if skip:  # the exchange went along with the gate before it: only the map is left to do
+            skip = False
+            a, b = rec.exchange
+            phys_to_logical[a], phys_to_logical[b] = phys_to_logical[b], phys_to_logical[a]
+            continue
         if rec.kind == 1:
             backend.convert(rec.dd)
             phys_to_logical = list(range(n_qubits))
         elif rec.kind == 2:
-            backend.apply(rec.dd)
+            if fuse is not None and at + 1 < len(records) and records[at + 1].kind == 3:
+                fuse(rec.dd, *records[at + 1].exchange)
+                skip = True
+            else:
+                backend.apply(rec.dd)
         elif rec.kind in (3, 4):
             a, b = rec.exchange
             if rec.kind == 3:
@@ -68,6 +80,14 @@ class GpuShard:
 
     def exchange(self, g, l):
         self.ctx.exchange_qubits(g, l, self.method)
+        self.exchanges += 1
+
+    def apply_then_exchange(self, dd, g, l):
+        if self.method != 0:  # the fused exchange is the peer-memory path
+            self.apply(dd)
+            self.exchange(g, l)
+            return
+        self.ctx.apply_many_exchange([dd], g, l)
         self.exchanges += 1
 
     def relabel(self, a, b):

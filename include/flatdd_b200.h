@@ -125,6 +125,14 @@ int fdd_get_option(const fdd_ctx* ctx, const char* key, long* value);
 int fdd_comm_unique_id(void* id128);
 int fdd_comm_init(fdd_ctx* ctx, const void* id128);
 int fdd_exchange_qubits(fdd_ctx* ctx, int global_physical_bit, int local_physical_bit, int method);
+/* A stretch of the schedule followed by the exchange the next gate needs, as if by fdd_apply_many / fdd_gate_apply_many and then
+ * fdd_exchange_qubits(..., 0) (the executor loop src/SwitchSimulator.cpp:386-412 up to a point where the partition
+ * include/dd/SwitchPackage.hpp:2146 has to change).  In one call the library can FUSE the two: when the stretch ends in a pass of
+ * the tile-resident kernel and the local bit is >= 5, that pass stores the half of its result that changes owner straight into
+ * the partner shard's buffer (peer memory over NVLink, per 512-byte segment) and the exchange costs no pass of its own
+ * ("block_fuse_exchange" = 0: never fuse; "fused_exchanges" counts them).  Every rank makes the same call. */
+int fdd_apply_many_exchange(fdd_ctx* ctx, const fdd_matdd* gates, int count, int global_physical_bit, int local_physical_bit);
+int fdd_gate_apply_many_exchange(fdd_ctx* ctx, const fdd_gate* const* gates, int count, int global_physical_bit, int local_physical_bit);
 /* Bookkeeping only: the logical qubits sitting at two physical bits trade names (an uncontrolled
  * SWAP gate absorbed into the layout, include/dd/Operations.hpp:611-620).  No data moves. */
 int fdd_relabel_qubits(fdd_ctx* ctx, int physical_bit_a, int physical_bit_b);

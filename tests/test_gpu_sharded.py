@@ -41,6 +41,8 @@ def _worker(rank, world, trace_path, port, out_dir, method, canonicalize):
             shard = GpuShard(ctx, exchange_method=method)
             l2p = replay(records, shard, n)
             assert list(ctx.permutation()) == l2p  # the context mirrors the layout
+            if rank == 0:
+                (Path(out_dir) / "stats.json").write_text(json.dumps({"exchanges": ctx.get_option("exchanges"), "fused_exchanges": ctx.get_option("fused_exchanges")}))
             if canonicalize:
                 ctx.canonicalize()
                 assert list(ctx.permutation()) == list(range(n))
@@ -77,6 +79,24 @@ def test_sharded_trace_vs_reference(case, method, tmp_path):
     got = run_sharded(SHARDED / case / "trace.bin", world, tmp_path, method=method)
     assert np.max(np.abs(got - want)) < 1e-10
     assert 1.0 - abs(np.vdot(got, want)) ** 2 / (np.vdot(got, got).real * np.vdot(want, want).real) < 1e-10
+
+
+def test_exchange_fused_into_the_preceding_pass(tmp_path):
+    """fdd_apply_many_exchange: the pass before an exchange writes the traded half straight into the partner's buffer.  The
+    replay hands every gate that is followed by an exchange to that call; on a dense-block schedule most exchanges then cost no
+    pass of their own, and the state is the reference's."""
+    trace = G.TRACES / "supremacy_n20_gpu_w2" / "trace.bin"
+    if n_gpus() < 2 or not trace.exists() or "supremacy_n20_f1" not in G.cases(G.TRAVEL):
+        pytest.skip("needs 2 GPUs and the travel goldens")
+    got = run_sharded(trace, 2, tmp_path)
+    stats = json.loads((Path(tmp_path) / "stats.json").read_text())
+    assert stats["exchanges"] > 0 and stats["fused_exchanges"] > 0, stats
+    if (G.TRAVEL / "supremacy_n20_f1" / "final_re.f64").exists():
+        fr, fi = G.final_state("supremacy_n20_f1", G.TRAVEL)
+        assert np.max(np.abs(got - (fr + 1j * fi))) < 1e-10
+    else:
+        idx, sr, si = G.samples("supremacy_n20_f1", G.TRAVEL)
+        assert np.max(np.abs(got[idx.astype(np.int64)] - (sr + 1j * si))) < 1e-10
 
 
 @pytest.mark.parametrize("case", [c for c in CASES if c.endswith("_w2")][:2])
