@@ -44,6 +44,13 @@ public:
     virtual void exchange(int /*globalPhysicalBit*/, int /*localPhysicalBit*/) {
         throw std::runtime_error("this backend holds an unsharded state");
     }
+    // a stretch of the schedule and the exchange that follows it in one boundary call: the GPU backend lets the stretch's last
+    // pass store the traded half straight into the partner shard (fdd_apply_many_exchange).  Default: the two calls.
+    virtual void applyManyThenExchange(const std::vector<FlatMatDD>& gates, const std::vector<int>& nOriginalGates, int globalPhysicalBit,
+                                       int localPhysicalBit) {
+        applyMany(gates, nOriginalGates);
+        exchange(globalPhysicalBit, localPhysicalBit);
+    }
     // device milliseconds of the last convert / apply when per-launch timing is on (0 otherwise)
     virtual double lastKernelMs() { return 0.0; }
     // the logical qubits at two physical bits trade names (absorbed SWAP gate); no data moves
@@ -94,6 +101,17 @@ public:
     void synchronize() override { fddCheck(fdd_synchronize(ctx_), "fdd_synchronize"); }
     void exchange(int globalPhysicalBit, int localPhysicalBit) override {
         fddCheck(fdd_exchange_qubits(ctx_, globalPhysicalBit, localPhysicalBit, exchangeMethod_), "fdd_exchange_qubits");
+    }
+    void applyManyThenExchange(const std::vector<FlatMatDD>& gates, const std::vector<int>& nOriginalGates, int globalPhysicalBit,
+                               int localPhysicalBit) override {
+        if (exchangeMethod_ != 0) { // the fused exchange is the peer-memory path
+            ArrayBackend::applyManyThenExchange(gates, nOriginalGates, globalPhysicalBit, localPhysicalBit);
+            return;
+        }
+        std::vector<fdd_matdd> views;
+        views.reserve(gates.size());
+        for (const auto& g : gates) views.push_back(view(g));
+        fddCheck(fdd_apply_many_exchange(ctx_, views.data(), static_cast<int>(views.size()), globalPhysicalBit, localPhysicalBit), "fdd_apply_many_exchange");
     }
     void relabel(int a, int b) override { fddCheck(fdd_relabel_qubits(ctx_, a, b), "fdd_relabel_qubits"); }
     void canonicalize() override { fddCheck(fdd_canonicalize(ctx_), "fdd_canonicalize"); }
@@ -208,8 +226,18 @@ public:
         inner_->synchronize();
     }
     void exchange(int globalPhysicalBit, int localPhysicalBit) override {
+        if (gates_.empty()) {
+            inner_->exchange(globalPhysicalBit, localPhysicalBit);
+            return;
+        }
+        inner_->applyManyThenExchange(gates_, originals_, globalPhysicalBit, localPhysicalBit); // the queued stretch takes the exchange along
+        gates_.clear();
+        originals_.clear();
+    }
+    void applyManyThenExchange(const std::vector<FlatMatDD>& gates, const std::vector<int>& nOriginalGates, int globalPhysicalBit,
+                               int localPhysicalBit) override {
         flush();
-        inner_->exchange(globalPhysicalBit, localPhysicalBit);
+        inner_->applyManyThenExchange(gates, nOriginalGates, globalPhysicalBit, localPhysicalBit);
     }
     void relabel(int a, int b) override {
         flush();
@@ -262,6 +290,12 @@ public:
     void exchange(int globalPhysicalBit, int localPhysicalBit) override {
         for (auto* s : sinks_) {
             s->exchange(globalPhysicalBit, localPhysicalBit);
+        }
+    }
+    void applyManyThenExchange(const std::vector<FlatMatDD>& gates, const std::vector<int>& nOriginalGates, int globalPhysicalBit,
+                               int localPhysicalBit) override {
+        for (auto* s : sinks_) {
+            s->applyManyThenExchange(gates, nOriginalGates, globalPhysicalBit, localPhysicalBit);
         }
     }
     void relabel(int a, int b) override {

@@ -984,8 +984,24 @@ private:
         const bool flatSchedule = !s.flats.empty();
         for (std::size_t i = 0; i < s.size(); ++i) {
             if (!s.layoutBefore[i].empty()) {
-                flush();
-                for (const auto& st : s.layoutBefore[i]) runLayoutStep(st);
+                std::size_t firstStep = 0;
+                if (!stretch.empty() && s.layoutBefore[i][0].exchange) {
+                    // the stretch takes the exchange that follows it along (ArrayBackend::applyManyThenExchange)
+                    const auto tg = Clock::now();
+                    backend->applyManyThenExchange(stretch, stretchOriginals, s.layoutBefore[i][0].a, s.layoutBefore[i][0].b);
+                    const double each = since(tg) / static_cast<double>(stretch.size());
+                    for (std::size_t k = 0; k < stretch.size(); ++k) timeRecord2.push_back(each);
+                    kernelMsTotal += backend->lastKernelMs();
+                    launches += stretch.size();
+                    stretch.clear();
+                    stretchOriginals.clear();
+                    ++exchanges;
+                    hostValid = false;
+                    firstStep = 1;
+                } else {
+                    flush();
+                }
+                for (std::size_t k = firstStep; k < s.layoutBefore[i].size(); ++k) runLayoutStep(s.layoutBefore[i][k]);
             }
             arrayPhaseOps += static_cast<std::size_t>(s.originals[i]);
             if (flatSchedule ? static_cast<bool>(s.flatIsIdentity[i]) : isIdentity(s.gates[i])) continue;
