@@ -90,6 +90,7 @@ struct fdd_gate {
     // dense-block path (block_kernel.cuh): the gate as a 2^k x 2^k block with its context table, when it is one
     std::unique_ptr<DenseBlock> block;
     double* dTable = nullptr;
+    bool tableBorrowed = false; // dTable points into an allocation somebody else frees (fdd_apply_many: one upload for the whole call)
     uint64_t serial = 0; // identifies the gate in the plan cache (pointers are reused by the allocator)
     const fdd_matdd* source = nullptr; // fdd_apply_many only: the caller's table while the call runs (lazy tables for the older kernels)
 };
@@ -520,7 +521,7 @@ void freeGate(fdd_gate* g, cudaStream_t stream) {
             cudaFree(g->dBlob);
         }
     }
-    if (g->dTable != nullptr) {
+    if (g->dTable != nullptr && !g->tableBorrowed) {
         cudaSetDevice(g->device);
         if (stream != nullptr) {
             cudaFreeAsync(g->dTable, stream);
@@ -1374,8 +1375,11 @@ static void applyManyHost(fdd_ctx* ctx, const fdd_matdd* gates, int count, Excha
         if (ctx == nullptr || (gates == nullptr && count > 0)) throw std::invalid_argument("null argument");
         useDevice(ctx);
         std::vector<fdd_gate*> owned;
+        double* arena = nullptr; // the matrix tables of all the call's blocks
         auto release = [&] {
             for (fdd_gate* g : owned) freeGate(g, ctx->stream); // stream ordered: released after the kernels have run
+            if (arena != nullptr) cudaFreeAsync(arena, ctx->stream);
+            arena = nullptr;
         };
         try {
             for (int i = 0; i < count; ++i) {
@@ -1405,12 +1409,35 @@ static void applyManyHost(fdd_ctx* ctx, const fdd_matdd* gates, int count, Excha
             } else {
                 for (int i = 0; i < count; ++i) blocks[static_cast<size_t>(i)] = extractBlock(ctx, gates[i]);
             }
+            // one allocation and one upload for the matrix tables of the whole call (48 small cudaMallocAsync / cudaMemcpyAsync pairs
+            // were a millisecond of host time in front of the first launch)
+            std::vector<size_t> offset(static_cast<size_t>(count), 0);
+            size_t total = 0;
+            for (int i = 0; i < count; ++i) {
+                if (!blocks[static_cast<size_t>(i)]) continue;
+                offset[static_cast<size_t>(i)] = total;
+                total += (blocks[static_cast<size_t>(i)]->table.size() * sizeof(double) + 255) & ~static_cast<size_t>(255);
+            }
+            if (total > 0) {
+                std::vector<double> staging(total / sizeof(double), 0.0);
+                for (int i = 0; i < count; ++i) {
+                    const auto& b = blocks[static_cast<size_t>(i)];
+                    if (b) std::memcpy(staging.data() + offset[static_cast<size_t>(i)] / sizeof(double), b->table.data(), b->table.size() * sizeof(double));
+                }
+                CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&arena), total, ctx->stream));
+                CUDA_TRY(cudaMemcpyAsync(arena, staging.data(), total, cudaMemcpyHostToDevice, ctx->stream)); // pageable: staged before the call returns
+            }
             for (int i = 0; i < count; ++i) {
                 auto g = new fdd_gate();
                 owned.push_back(g);
                 g->device = ctx->device;
                 g->source = &gates[i]; // the older kernels' tables are only made if a launch needs them
-                uploadBlock(ctx, g, std::move(blocks[static_cast<size_t>(i)]));
+                if (blocks[static_cast<size_t>(i)]) {
+                    g->dTable = arena + offset[static_cast<size_t>(i)] / sizeof(double);
+                    g->tableBorrowed = true;
+                    g->block = std::move(blocks[static_cast<size_t>(i)]);
+                    g->serial = ++ctx->gateSerial;
+                }
             }
             applyGates(ctx, owned.data(), count, false, ex);
         } catch (...) {

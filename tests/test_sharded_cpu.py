@@ -79,6 +79,41 @@ def test_sharded_schedule_on_global_model(case):
     assert sum(r.kind == 3 for r in records) == m["trace"]["exchanges"]
 
 
+class FusingModel(GlobalModel):
+    """A backend that takes a gate and the exchange after it in one call, like GpuShard.apply_then_exchange (fdd_apply_many_exchange)."""
+
+    def __init__(self, n, n_local):
+        super().__init__(n, n_local)
+        self.fused, self.plain_exchanges = 0, 0
+
+    def exchange(self, pg, pl):
+        self.plain_exchanges += 1
+        super().exchange(pg, pl)
+
+    def apply_then_exchange(self, dd, pg, pl):
+        self.apply(dd)
+        GlobalModel.exchange(self, pg, pl)
+        self.fused += 1
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_replay_hands_a_gate_and_the_exchange_after_it_to_one_call(case):
+    """replay(): a gate record followed by an exchange record goes to apply_then_exchange when the backend has it; the layout map
+    and the final state are those of the two separate calls, and every exchange is accounted for exactly once."""
+    m, want = reference_final(case)
+    n, records = read_trace(SHARDED / case / "trace.bin")
+    n_local = n - int(np.log2(m["trace"]["world"]))
+    plain, fusing = GlobalModel(n, n_local), FusingModel(n, n_local)
+    l2p_plain = replay(records, plain, n)
+    l2p = replay(records, fusing, n)
+    assert l2p == l2p_plain
+    assert np.array_equal(fusing.re, plain.re) and np.array_equal(fusing.im, plain.im)
+    assert fusing.fused + fusing.plain_exchanges == sum(r.kind == 3 for r in records)
+    follows_gate = sum(1 for a, b in zip(records, records[1:]) if a.kind == 2 and b.kind == 3)
+    assert fusing.fused == follows_gate
+    assert np.max(np.abs(to_logical_order(fusing.re + 1j * fusing.im, l2p) - want)) < 1e-12
+
+
 def test_to_logical_order_roundtrip():
     rng = np.random.default_rng(0)
     n = 6
