@@ -179,7 +179,7 @@ def reference_arm(args) -> int:
               f"({runs[0]['launches']} fused DMAVM calls, conversion included), reference CLI --fuse 1 -t {threads}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": warmup, "ms_per_step": 1e3 * secs / max(1, len(runs)), "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": 1e3 * secs / max(1, len(runs)), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{WORKLOAD} array phase (bounded sample)", "n_qubits": 26, "fusion": "reference greedy (--fuse 1)",
                    "host_cores": os.cpu_count(), "threads": threads},
