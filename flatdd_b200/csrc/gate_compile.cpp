@@ -435,7 +435,7 @@ struct CostKnobs {
 
 double costGpuNs(const CompiledGate& c, double hbmGBs, double fp64GFlops) {
     // Time of one launch as a multiple of the HBM time of one read + one write pass (0.33 ms at n = 26).
-    // Two regimes, both fitted to the tile kernel on B200 (profiles/r01_cost_model_fit.txt):
+    // Two regimes, both fitted to the tile kernel on B200 (per-gate device times of round 1: profiles/r01_per_gate_supremacy_n26.csv, profiles/r01b_per_gate_supremacy_n26_fuse4.csv):
     //  * KNOWN-FAST classes — the block does not depend on qubits outside its tile ("uniform"), its low
     //    levels are untouched or one sub table serves the whole gate, and its upper part is either small
     //    (<= 4 sources per segment) or complete (2^TB sources, TB <= 4: the register path).  Measured
